@@ -1,0 +1,256 @@
+"""CPU oracle for the DA-MVSNet per-stage cost-volume hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in ``damvsnet_b200/`` imports this file; only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may.  The product path is the CUDA extension and it
+fails loudly when that extension is missing.
+
+This is a restatement, in plain fp32 torch-CPU tensor arithmetic, of what the
+reference computes in ``DepthNet.forward`` (reference models/cas_mvsnet.py:18-134)
+and the functions it calls.  Each function cites the reference lines it follows.
+The arithmetic of the reference lives in PyTorch library ops (``F.grid_sample``,
+``nn.Conv3d``, ``nn.BatchNorm3d``, ``F.softmax`` ...); the warp, the view-weight
+network, the BatchNorm fold and the regression head are restated here in closed
+form (no ``grid_sample``, no ``nn.Module``), the 3-D convolutions call
+``F.conv3d`` / ``F.conv_transpose3d`` directly.
+
+Parity pinning: the reference ships no tests or golden vectors (SURVEY.md
+section 4), so the oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF, run
+in the build container by ``tests/golden/make_golden.py`` (which imports the
+unmodified reference from /root/reference) and committed as
+``tests/golden/*.npz``; ``tests/test_oracle_golden.py`` checks this file against
+those fixtures on every CPU test run.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+BN_EPS = 1e-5  # nn.BatchNorm3d default, reference models/module.py:141,184
+
+
+# --------------------------------------------------------------------------
+# projection + warp
+# --------------------------------------------------------------------------
+def compose_projection(proj_pair: torch.Tensor) -> torch.Tensor:
+    """[B,2,4,4] (extrinsic, intrinsic) -> [B,4,4] with rows 0-2 = K @ E[:3,:4].
+
+    Reference models/cas_mvsnet.py:44-47.
+    """
+    out = proj_pair[:, 0].clone()
+    out[:, :3, :4] = torch.matmul(proj_pair[:, 1, :3, :3], proj_pair[:, 0, :3, :4])
+    return out
+
+
+def relative_projection(src_proj: torch.Tensor, ref_proj: torch.Tensor):
+    """rot [B,3,3], trans [B,3] of ``src_proj @ inverse(ref_proj)``.
+
+    Reference models/module.py:308-310.
+    """
+    proj = torch.matmul(src_proj, torch.inverse(ref_proj))
+    return proj[:, :3, :3].contiguous(), proj[:, :3, 3].contiguous()
+
+
+def warp_coordinates(rot: torch.Tensor, trans: torch.Tensor, depth_values: torch.Tensor,
+                     height: int, width: int):
+    """Un-normalised source sample coordinates (ix, iy), each [B,D,H*W].
+
+    Reference models/module.py:312-325 builds a grid normalised by (W-1)/2 and
+    (H-1)/2; ``F.grid_sample`` is then called with its default
+    ``align_corners=False`` (models/module.py:328-329), whose un-normalisation is
+    ``((g + 1) * size - 1) / 2``.  Both steps are kept, in that order, so the
+    rounding matches.
+    """
+    b = rot.shape[0]
+    d = depth_values.shape[1]
+    y, x = torch.meshgrid(torch.arange(0, height, dtype=torch.float32),
+                          torch.arange(0, width, dtype=torch.float32), indexing="ij")
+    xyz = torch.stack((x.reshape(-1), y.reshape(-1), torch.ones(height * width)))  # [3,HW]
+    rot_xyz = torch.matmul(rot, xyz.unsqueeze(0).expand(b, -1, -1))                 # [B,3,HW]
+    dv = depth_values.reshape(b, 1, d, -1)                                          # [B,1,D,HW or 1]
+    proj_xyz = rot_xyz.unsqueeze(2) * dv + trans.view(b, 3, 1, 1)                   # [B,3,D,HW]
+    px = proj_xyz[:, 0] / proj_xyz[:, 2]
+    py = proj_xyz[:, 1] / proj_xyz[:, 2]
+    gx = px / ((width - 1) / 2) - 1
+    gy = py / ((height - 1) / 2) - 1
+    ix = ((gx + 1) * width - 1) / 2
+    iy = ((gy + 1) * height - 1) / 2
+    return ix, iy
+
+
+def bilinear_zeros(src: torch.Tensor, ix: torch.Tensor, iy: torch.Tensor) -> torch.Tensor:
+    """Bilinear sample with zero padding per tap.  src [B,C,H,W]; ix, iy [B,P].
+
+    Restates ATen's grid_sampler_2d (bilinear, padding_mode='zeros'): taps at
+    floor and floor+1, weights from the unclipped coordinate, an out-of-range
+    tap contributes zero.
+    """
+    b, c, h, w = src.shape
+    x0 = torch.floor(ix)
+    y0 = torch.floor(iy)
+    wx1 = ix - x0
+    wy1 = iy - y0
+    wx0 = 1.0 - wx1
+    wy0 = 1.0 - wy1
+    flat = src.reshape(b, c, h * w)
+    out = torch.zeros(b, c, ix.shape[1], dtype=src.dtype)
+    for dy, wy in ((0, wy0), (1, wy1)):
+        for dx, wx in ((0, wx0), (1, wx1)):
+            xi = x0 + dx
+            yi = y0 + dy
+            ok = (xi >= 0) & (xi <= w - 1) & (yi >= 0) & (yi <= h - 1)
+            lin = (yi.clamp(0, h - 1) * w + xi.clamp(0, w - 1)).long()
+            tap = torch.gather(flat, 2, lin.unsqueeze(1).expand(-1, c, -1))
+            out = out + tap * (wy * wx * ok.to(src.dtype)).unsqueeze(1)
+    return out
+
+
+def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.Tensor,
+                 depth_values: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] source features -> [B,C,D,H,W] warped volume.
+
+    Reference models/module.py:297-332.  ``depth_values`` is [B,D] or [B,D,H,W].
+    """
+    b, c, h, w = src_fea.shape
+    d = depth_values.shape[1]
+    rot, trans = relative_projection(src_proj, ref_proj)
+    ix, iy = warp_coordinates(rot, trans, depth_values, h, w)
+    ix = ix.expand(b, d, h * w).reshape(b, -1)
+    iy = iy.expand(b, d, h * w).reshape(b, -1)
+    return bilinear_zeros(src_fea, ix, iy).view(b, c, d, h, w)
+
+
+# --------------------------------------------------------------------------
+# BatchNorm fold, view-weight net, aggregation
+# --------------------------------------------------------------------------
+def bn_affine(sd: Dict[str, torch.Tensor], prefix: str):
+    """Eval-mode BatchNorm as y = x * scale + shift (reference models/module.py:141,150)."""
+    scale = sd[prefix + ".weight"] / torch.sqrt(sd[prefix + ".running_var"] + BN_EPS)
+    shift = sd[prefix + ".bias"] - sd[prefix + ".running_mean"] * scale
+    return scale, shift
+
+
+def view_weight(sq: torch.Tensor, sd: Dict[str, torch.Tensor], stage_idx: int) -> torch.Tensor:
+    """AggWeightNetVolume.forward in eval mode: [B,C,D,H,W] -> [B,1,D,H,W].
+
+    Reference models/module.py:544-563: two 1x1x1 Conv3d(bias=False)+BN+ReLU
+    blocks (``w_net``); ``conv0`` is constructed but never called.
+    """
+    p = f"DepthNet.weight_net.{stage_idx}.w_net."
+    w1 = sd[p + "0.conv.weight"].view(1, -1, 1, 1, 1)
+    s1, b1 = bn_affine(sd, p + "0.bn")
+    w2 = sd[p + "1.conv.weight"].view(())
+    s2, b2 = bn_affine(sd, p + "1.bn")
+    s = (sq * w1).sum(dim=1, keepdim=True)
+    a = torch.relu(s * s1 + b1)
+    return torch.relu((a * w2) * s2 + b2)
+
+
+def aggregate(features: Sequence[torch.Tensor], proj_matrices: torch.Tensor, depth_values: torch.Tensor,
+              mode: str, sd: Optional[Dict[str, torch.Tensor]] = None, stage_idx: int = 0) -> torch.Tensor:
+    """Multi-view cost volume [B,C,D,H,W].  Reference models/cas_mvsnet.py:19-87."""
+    projs = torch.unbind(proj_matrices, 1)
+    assert len(features) == len(projs)
+    n = len(features)
+    ref, srcs = features[0], features[1:]
+    ref_proj = compose_projection(projs[0])
+    d = depth_values.shape[1]
+    ref_vol = ref.unsqueeze(2).expand(-1, -1, d, -1, -1)
+    if mode == "variance":
+        vsum = ref_vol.clone()
+        vsq = ref_vol ** 2
+        for src, pm in zip(srcs, projs[1:]):
+            wv = homo_warping(src, compose_projection(pm), ref_proj, depth_values)
+            vsum = vsum + wv
+            vsq = vsq + wv ** 2
+        return vsq / n - (vsum / n) ** 2                      # cas_mvsnet.py:85
+    if mode == "adaptive":
+        acc = None
+        for src, pm in zip(srcs, projs[1:]):
+            wv = homo_warping(src, compose_projection(pm), ref_proj, depth_values)
+            sq = (ref_vol - wv) ** 2                          # cas_mvsnet.py:66
+            wt = view_weight(sq, sd, stage_idx)               # cas_mvsnet.py:71
+            term = (wt + 1) * sq
+            acc = term if acc is None else acc + term         # cas_mvsnet.py:73-76
+        return acc / (n - 1)                                  # cas_mvsnet.py:87
+    raise ValueError(mode)
+
+
+# --------------------------------------------------------------------------
+# CostRegNet
+# --------------------------------------------------------------------------
+def conv_block(x, sd, prefix, stride=1):
+    """Conv3d(k3, padding=1, bias=False) + BN(eval) + ReLU.  Reference models/module.py:117-159."""
+    y = F.conv3d(x, sd[prefix + ".conv.weight"], None, stride=stride, padding=1)
+    s, b = bn_affine(sd, prefix + ".bn")
+    return torch.relu(y * s.view(1, -1, 1, 1, 1) + b.view(1, -1, 1, 1, 1))
+
+
+def deconv_block(x, sd, prefix):
+    """ConvTranspose3d(k3, s2, p1, op1, bias=False) + BN(eval) + ReLU.  Reference models/module.py:161-202."""
+    y = F.conv_transpose3d(x, sd[prefix + ".conv.weight"], None, stride=2, padding=1, output_padding=1)
+    s, b = bn_affine(sd, prefix + ".bn")
+    return torch.relu(y * s.view(1, -1, 1, 1, 1) + b.view(1, -1, 1, 1, 1))
+
+
+def cost_reg_net(x: torch.Tensor, sd: Dict[str, torch.Tensor], stage_idx: int) -> torch.Tensor:
+    """[B,C,D,H,W] -> logits [B,1,D,H,W].  Reference models/module.py:510-541."""
+    p = f"cost_regularization.{stage_idx}."
+    c0 = conv_block(x, sd, p + "conv0")
+    c2 = conv_block(conv_block(c0, sd, p + "conv1", 2), sd, p + "conv2")
+    c4 = conv_block(conv_block(c2, sd, p + "conv3", 2), sd, p + "conv4")
+    y = conv_block(conv_block(c4, sd, p + "conv5", 2), sd, p + "conv6")
+    y = c4 + deconv_block(y, sd, p + "conv7")
+    y = c2 + deconv_block(y, sd, p + "conv9")
+    y = c0 + deconv_block(y, sd, p + "conv11")
+    return F.conv3d(y, sd[p + "prob.weight"], None, stride=1, padding=1)
+
+
+# --------------------------------------------------------------------------
+# regression head
+# --------------------------------------------------------------------------
+def regress_head(logits: torch.Tensor, depth_values: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """logits [B,D,H,W], depth_values [B,D,H,W] -> the five per-stage outputs.
+
+    Reference models/cas_mvsnet.py:105-134 and models/module.py:609-615.
+    """
+    b, d, h, w = logits.shape
+    m = logits.max(dim=1, keepdim=True).values
+    e = torch.exp(logits - m)
+    prob = e / e.sum(dim=1, keepdim=True)                                   # F.softmax(dim=1)
+    depth = (prob * depth_values).sum(dim=1)                                # depth_regression
+    # confidence: sum of p over [idx-1, idx+2], zero outside [0,D-1] (cas_mvsnet.py:113-118)
+    padded = F.pad(prob, (0, 0, 0, 0, 1, 2))
+    sum4 = padded[:, 0:d] + padded[:, 1:d + 1] + padded[:, 2:d + 2] + padded[:, 3:d + 3]
+    k = torch.arange(d, dtype=torch.float32).view(1, d, 1, 1)
+    idx = (prob * k).sum(dim=1).long().clamp(0, d - 1)
+    conf = torch.gather(sum4, 1, idx.unsqueeze(1)).squeeze(1)
+    var = 3 * torch.sum((depth_values - depth.unsqueeze(1)) ** 2 * prob, dim=1) ** 0.5   # cas_mvsnet.py:121-124
+    return {"depth": depth, "photometric_confidence": conf, "variance": var,
+            "prob_volume": prob, "depth_values": depth_values}
+
+
+def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tensor:
+    """Reference models/module.py:609-615."""
+    if depth_values.dim() <= 2:
+        depth_values = depth_values.view(*depth_values.shape, 1, 1)
+    return torch.sum(p * depth_values, 1)
+
+
+# --------------------------------------------------------------------------
+# whole stage
+# --------------------------------------------------------------------------
+def depthnet_forward(stage_idx: int, features: List[torch.Tensor], proj_matrices: torch.Tensor,
+                     depth_values: torch.Tensor, sd: Dict[str, torch.Tensor], mode: str = "adaptive",
+                     return_volume: bool = False) -> Dict[str, torch.Tensor]:
+    """DepthNet.forward for one stage (reference models/cas_mvsnet.py:18-134), eval-mode BN."""
+    assert depth_values.dim() == 4
+    vol = aggregate(features, proj_matrices, depth_values, mode, sd, stage_idx)
+    logits = cost_reg_net(vol, sd, stage_idx).squeeze(1)
+    out = regress_head(logits, depth_values)
+    if return_volume:
+        out["volume"] = vol
+        out["logits"] = logits
+    return out
