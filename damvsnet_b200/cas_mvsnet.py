@@ -1,0 +1,65 @@
+"""Host-side mirror of the reference's ``models/cas_mvsnet.py`` hot path: ``DepthNet``.
+
+``DepthNet.forward`` keeps the reference signature and output dict
+(models/cas_mvsnet.py:18, :133-134) and runs three native kernels per stage:
+fused warp+aggregate -> CostRegNet conv blocks -> softmax/regression head.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .module import AggWeightNetVolume, CostRegNet
+
+__all__ = ["DepthNet"]
+
+
+class DepthNet(nn.Module):
+    """Per-stage cost-volume pipeline (reference models/cas_mvsnet.py:10-134)."""
+
+    def __init__(self, mode="adaptive", in_channels=None):
+        super().__init__()
+        self.mode = mode
+        assert mode in ("variance", "adaptive"), "Don't support {}!".format(mode)
+        if self.mode == "adaptive":
+            self.weight_net = nn.ModuleList([AggWeightNetVolume(in_channels[i]) for i in range(len(in_channels))])
+
+    @staticmethod
+    def stage_rot_trans(proj_matrices: torch.Tensor) -> torch.Tensor:
+        """[B,N,2,4,4] -> [N-1,B,12]: per source view, rows 0-2 of P_src @ inverse(P_ref)
+        with P = [K @ E[:3,:4]; E[3]] (reference models/cas_mvsnet.py:44-47, models/module.py:308-310)."""
+        p = ops.compose_projection(proj_matrices.float())          # [B,N,4,4]
+        ref = p[:, 0:1]                                             # [B,1,4,4]
+        rt = ops.relative_rot_trans(p[:, 1:], ref.expand(-1, p.shape[1] - 1, -1, -1).contiguous())  # [B,N-1,12]
+        return rt.permute(1, 0, 2).contiguous()
+
+    def cost_volume(self, stage_idx: int, features: List[torch.Tensor], proj_matrices: torch.Tensor,
+                    depth_values: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> ops.G8Volume:
+        """Aggregated cost volume (reference models/cas_mvsnet.py:30-87) as a G8 volume."""
+        rot_trans = self.stage_rot_trans(proj_matrices)
+        nhwc = [ops.features_to_nhwc(f) for f in features]
+        wnet = self.weight_net[stage_idx].folded() if self.mode == "adaptive" else None
+        return ops.warp_aggregate(nhwc[0], nhwc[1:], rot_trans, depth_values, wnet, self.mode,
+                                  out_dtype or ops.volume_dtype())
+
+    def forward(self, stage_idx, features, proj_matrices, depth_values, num_depth, cost_regularization,
+                prob_volume_init=None) -> Dict[str, torch.Tensor]:
+        assert len(features) == proj_matrices.shape[1], "Different number of images and projection matrices"
+        assert depth_values.shape[1] == num_depth, "depth_values.shape[1]:{}  num_depth:{}".format(
+            depth_values.shape[1], num_depth)
+        if not isinstance(cost_regularization, CostRegNet):
+            raise TypeError("cost_regularization must be a damvsnet_b200 CostRegNet")
+        volume = self.cost_volume(stage_idx, features, proj_matrices, depth_values)
+        logits = cost_regularization.forward_g8(volume)                       # [B,D,h,w] fp32
+        if prob_volume_init is not None:                                       # dead in the reference (always None)
+            logits = logits + prob_volume_init
+        dv = depth_values
+        if dv.dim() == 2:
+            b, _, h, w = logits.shape
+            dv = dv.view(b, -1, 1, 1).expand(-1, -1, h, w).contiguous()
+        prob, depth, conf, var = ops.softmax_regress(logits, dv)
+        return {"depth": depth, "photometric_confidence": conf, "variance": var,
+                "prob_volume": prob, "depth_values": depth_values}

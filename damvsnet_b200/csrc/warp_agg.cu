@@ -1,0 +1,278 @@
+// Fused homography warp + multi-view aggregation (forward).
+//
+// Replaces the source-view loop of DepthNet.forward (reference
+// models/cas_mvsnet.py:30-87) together with homo_warping
+// (models/module.py:297-332) and AggWeightNetVolume in eval mode
+// (models/module.py:544-563).  The reference materialises, per source view, a
+// sampling grid, a warped [B,C,D,h,w] volume, its squared difference to a
+// repeated reference volume and a weight volume; here each depth plane's
+// projection is built in registers, the four bilinear taps are gathered from the
+// NHWC source feature map as 16-byte vectors, and the aggregate is accumulated
+// on the fly, so the only HBM traffic is the feature maps (read, mostly through
+// L2), the hypotheses (read once) and the cost volume (written once, G8 layout,
+// optionally bf16).
+//
+// Algorithmic bytes per launch: N*C*h*w*4 + D*h*w*4 read, C*D*h*w*sizeof(out) written.
+//
+// Mapping: a thread owns (pixel, 4 consecutive channels) and walks the D
+// hypotheses of its pixel; the C/4 lanes of a pixel are adjacent in the warp, so
+// one tap of one pixel is a single contiguous C*4-byte segment (a full 128-byte
+// line for C=32) and the channel reduction of the view-weight net is a
+// log2(C/4)-step xor shuffle.  A warp covers 32/(C/4) consecutive pixels of a
+// row, a 256-thread CTA a (2*that) x 4 pixel patch, which keeps the source
+// footprint of a CTA compact as it slides along the epipolar lines.
+//
+// Sampling semantics are the reference's, quirk included:
+// the grid is normalised with (W-1)/2 but sampled with align_corners=False, no
+// z>0 mask, no epsilon in the perspective divide, zero padding per tap.
+#include "common.cuh"
+
+namespace damvs {
+
+constexpr int kMaxSrc = 15;
+
+struct WarpAggParams {
+  const float* ref;
+  const float* src[kMaxSrc];
+  const float* rot_trans;  // [n_src][B][12]
+  const float* hyp;        // [B][D][H][W] or [B][D]
+  const float* wnet;       // [C+5] or null
+  void* out;               // G8 [B][C/8][D][H][W][8]
+  int B, n_src, D, H, W, per_pixel;
+};
+
+// source coordinates of reference pixel (x,y) at depth d, exactly in the
+// reference's operation order (mul, add, div kept un-contracted)
+__device__ __forceinline__ void project(const float* rt, float rx, float ry, float rz, float d, float half_w,
+                                        float half_h, float fw, float fh, float& ix, float& iy) {
+  float px = __fadd_rn(__fmul_rn(rx, d), rt[9]);
+  float py = __fadd_rn(__fmul_rn(ry, d), rt[10]);
+  float pz = __fadd_rn(__fmul_rn(rz, d), rt[11]);
+  float u = __fdiv_rn(px, pz);
+  float v = __fdiv_rn(py, pz);
+  float gx = __fadd_rn(__fdiv_rn(u, half_w), -1.f);  // models/module.py:323
+  float gy = __fadd_rn(__fdiv_rn(v, half_h), -1.f);  // models/module.py:324
+  // ATen grid_sampler_unnormalize, align_corners=False
+  ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gx, 1.f), fw), -1.f), 0.5f);
+  iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gy, 1.f), fh), -1.f), 0.5f);
+}
+
+// bilinear sample of 4 channels with zero padding per tap (ATen grid_sampler_2d order nw, ne, sw, se)
+__device__ __forceinline__ float4 sample4(const float* __restrict__ img, int H, int W, int C, int c0, float ix,
+                                          float iy) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // NaN / far-out-of-range coordinates sample nothing (ATen returns NaN for NaN coordinates; the
+  // synthetic inputs keep z != 0)
+  if (!(ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H)) return acc;
+  float fx0 = floorf(ix), fy0 = floorf(iy);
+  int x0 = (int)fx0, y0 = (int)fy0;
+  float fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+  float wnw = (fx1 - ix) * (fy1 - iy);
+  float wne = (ix - fx0) * (fy1 - iy);
+  float wsw = (fx1 - ix) * (iy - fy0);
+  float wse = (ix - fx0) * (iy - fy0);
+  bool xl = x0 >= 0, xr = x0 + 1 < W, yt = y0 >= 0, yb = y0 + 1 < H;
+  const float* p = img + ((long long)y0 * W + x0) * C + c0;
+  float4 t;
+  if (yt && xl) {
+    t = __ldg(reinterpret_cast<const float4*>(p));
+    acc.x += t.x * wnw; acc.y += t.y * wnw; acc.z += t.z * wnw; acc.w += t.w * wnw;
+  }
+  if (yt && xr) {
+    t = __ldg(reinterpret_cast<const float4*>(p + C));
+    acc.x += t.x * wne; acc.y += t.y * wne; acc.z += t.z * wne; acc.w += t.w * wne;
+  }
+  if (yb && xl) {
+    t = __ldg(reinterpret_cast<const float4*>(p + (long long)W * C));
+    acc.x += t.x * wsw; acc.y += t.y * wsw; acc.z += t.z * wsw; acc.w += t.w * wsw;
+  }
+  if (yb && xr) {
+    t = __ldg(reinterpret_cast<const float4*>(p + (long long)W * C + C));
+    acc.x += t.x * wse; acc.y += t.y * wse; acc.z += t.z * wse; acc.w += t.w * wse;
+  }
+  return acc;
+}
+
+template <int C, int MODE, typename OutT>
+__global__ void __launch_bounds__(256) warp_agg_kernel(const WarpAggParams P) {
+  constexpr int LPP = C / 4;     // lanes per pixel
+  constexpr int PPW = 32 / LPP;  // pixels per warp (along x)
+  constexpr int TW = 2 * PPW, TH = 4;
+  __shared__ float s_rt[kMaxSrc * 12];
+  __shared__ float s_wnet[C + 5];
+
+  const int b = blockIdx.z;
+  const int H = P.H, W = P.W, D = P.D, n_src = P.n_src;
+  for (int i = threadIdx.x; i < n_src * 12; i += blockDim.x) {
+    int v = i / 12, j = i - v * 12;
+    s_rt[i] = P.rot_trans[((long long)v * P.B + b) * 12 + j];
+  }
+  if (MODE == DAMVS_AGG_ADAPTIVE)
+    for (int i = threadIdx.x; i < C + 5; i += blockDim.x) s_wnet[i] = P.wnet[i];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = lane % LPP;  // channel quad
+  const int px = blockIdx.x * TW + (warp & 1) * PPW + lane / LPP;
+  const int py = blockIdx.y * TH + (warp >> 1);
+  const bool live = px < W && py < H;
+  const int x = live ? px : 0, y = live ? py : 0;
+  const int c0 = q * 4;
+  const long long HW = (long long)H * W;
+  const long long img_stride = HW * C;
+
+  const float4 rf = __ldg(reinterpret_cast<const float4*>(P.ref + (long long)b * img_stride + ((long long)y * W + x) * C + c0));
+  const float fx = (float)x, fy = (float)y;
+  const float half_w = (float)((W - 1) / 2.0), half_h = (float)((H - 1) / 2.0);
+  const float fw = (float)W, fh = (float)H;
+  float w1[4] = {0.f, 0.f, 0.f, 0.f};
+  float s1 = 0.f, b1 = 0.f, w2 = 0.f, s2 = 0.f, b2 = 0.f;
+  if (MODE == DAMVS_AGG_ADAPTIVE) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w1[j] = s_wnet[c0 + j];
+    s1 = s_wnet[C]; b1 = s_wnet[C + 1]; w2 = s_wnet[C + 2]; s2 = s_wnet[C + 3]; b2 = s_wnet[C + 4];
+  }
+  const float* hyp = P.per_pixel ? P.hyp + (long long)b * D * HW + (long long)y * W + x : P.hyp + (long long)b * D;
+  const long long hyp_stride = P.per_pixel ? HW : 1;
+  OutT* out = reinterpret_cast<OutT*>(P.out) + g8_offset(b, q >> 1, 0, y, x, C / 8, D, H, W) + (q & 1) * 4;
+  const long long out_stride = HW * 8;
+  const float inv_n = 1.f / (float)(n_src + 1), inv_nsrc = 1.f / (float)n_src;
+
+  for (int d = 0; d < D; ++d) {
+    const float dep = __ldg(hyp + d * hyp_stride);
+    float a0, a1, a2, a3, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+    if (MODE == DAMVS_AGG_VARIANCE) {
+      a0 = rf.x; a1 = rf.y; a2 = rf.z; a3 = rf.w;
+      q0 = rf.x * rf.x; q1 = rf.y * rf.y; q2 = rf.z * rf.z; q3 = rf.w * rf.w;
+    } else {
+      a0 = a1 = a2 = a3 = 0.f;
+    }
+    for (int v = 0; v < n_src; ++v) {
+      const float* rt = s_rt + v * 12;
+      // rot @ [x, y, 1]  (models/module.py:317)
+      float rx = fmaf(rt[0], fx, fmaf(rt[1], fy, rt[2]));
+      float ry = fmaf(rt[3], fx, fmaf(rt[4], fy, rt[5]));
+      float rz = fmaf(rt[6], fx, fmaf(rt[7], fy, rt[8]));
+      float ix, iy;
+      project(rt, rx, ry, rz, dep, half_w, half_h, fw, fh, ix, iy);
+      float4 wv = sample4(P.src[v] + (long long)b * img_stride, H, W, C, c0, ix, iy);
+      if (MODE == DAMVS_AGG_VARIANCE) {
+        a0 += wv.x; a1 += wv.y; a2 += wv.z; a3 += wv.w;
+        q0 += wv.x * wv.x; q1 += wv.y * wv.y; q2 += wv.z * wv.z; q3 += wv.w * wv.w;
+      } else {
+        float e0 = rf.x - wv.x, e1 = rf.y - wv.y, e2 = rf.z - wv.z, e3 = rf.w - wv.w;
+        e0 *= e0; e1 *= e1; e2 *= e2; e3 *= e3;                       // cas_mvsnet.py:66
+        float s = w1[0] * e0 + w1[1] * e1 + w1[2] * e2 + w1[3] * e3;  // 1x1x1 conv C->1
+#pragma unroll
+        for (int o = LPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        float a = fmaxf(s * s1 + b1, 0.f);                            // BN + ReLU
+        float wt = fmaxf((a * w2) * s2 + b2, 0.f) + 1.f;              // conv 1->1, BN, ReLU; (weight + 1)
+        a0 += wt * e0; a1 += wt * e1; a2 += wt * e2; a3 += wt * e3;   // cas_mvsnet.py:73-76
+      }
+    }
+    if (MODE == DAMVS_AGG_VARIANCE) {
+      float m0 = a0 * inv_n, m1 = a1 * inv_n, m2 = a2 * inv_n, m3 = a3 * inv_n;
+      a0 = q0 * inv_n - m0 * m0; a1 = q1 * inv_n - m1 * m1;            // cas_mvsnet.py:85
+      a2 = q2 * inv_n - m2 * m2; a3 = q3 * inv_n - m3 * m3;
+    } else {
+      a0 *= inv_nsrc; a1 *= inv_nsrc; a2 *= inv_nsrc; a3 *= inv_nsrc;  // cas_mvsnet.py:87
+    }
+    if (live) store4(out + d * out_stride, a0, a1, a2, a3);
+  }
+}
+
+// stand-alone homo_warping: [B,H,W,C] -> [B,C,D,H,W] fp32 (reference output layout)
+__global__ void __launch_bounds__(256) homo_warp_kernel(const float* __restrict__ src, const float* __restrict__ rot_trans,
+                                                        const float* __restrict__ hyp, float* __restrict__ out,
+                                                        int C, int D, int H, int W, int per_pixel) {
+  const int b = blockIdx.z;
+  const long long HW = (long long)H * W;
+  long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= HW) return;
+  const int d = blockIdx.y;
+  const int y = (int)(pix / W), x = (int)(pix - (long long)y * W);
+  float rt[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) rt[j] = __ldg(rot_trans + b * 12 + j);
+  const float fx = (float)x, fy = (float)y;
+  float rx = fmaf(rt[0], fx, fmaf(rt[1], fy, rt[2]));
+  float ry = fmaf(rt[3], fx, fmaf(rt[4], fy, rt[5]));
+  float rz = fmaf(rt[6], fx, fmaf(rt[7], fy, rt[8]));
+  float dep = per_pixel ? __ldg(hyp + ((long long)b * D + d) * HW + pix) : __ldg(hyp + b * D + d);
+  float ix, iy;
+  project(rt, rx, ry, rz, dep, (float)((W - 1) / 2.0), (float)((H - 1) / 2.0), (float)W, (float)H, ix, iy);
+  const float* img = src + (long long)b * HW * C;
+  float* o = out + (((long long)b * C) * D + d) * HW + pix;
+  for (int c0 = 0; c0 < C; c0 += 4) {
+    float4 v = sample4(img, H, W, C, c0, ix, iy);
+    o[(long long)(c0 + 0) * D * HW] = v.x;
+    o[(long long)(c0 + 1) * D * HW] = v.y;
+    o[(long long)(c0 + 2) * D * HW] = v.z;
+    o[(long long)(c0 + 3) * D * HW] = v.w;
+  }
+}
+
+template <int C, int MODE>
+static int launch_warp_agg(const WarpAggParams& P, int out_dtype, cudaStream_t st) {
+  constexpr int TW = 2 * (32 / (C / 4)), TH = 4;
+  dim3 grid((P.W + TW - 1) / TW, (P.H + TH - 1) / TH, P.B);
+  if (out_dtype == DAMVS_F32)
+    warp_agg_kernel<C, MODE, float><<<grid, 256, 0, st>>>(P);
+  else
+    warp_agg_kernel<C, MODE, __nv_bfloat16><<<grid, 256, 0, st>>>(P);
+  DAMVS_LAUNCH_OK("warp_agg kernel");
+  return DAMVS_OK;
+}
+
+}  // namespace damvs
+
+using namespace damvs;
+
+extern "C" int damvs_warp_agg_fwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src,
+                                  const float* rot_trans, const float* depth_hyp, const float* wnet, void* out_vol,
+                                  int B, int C, int D, int H, int W, int mode, int per_pixel_hyp, int out_dtype,
+                                  void* stream) {
+  DAMVS_REQUIRE(ref_nhwc && src_nhwc && rot_trans && depth_hyp && out_vol, "warp_agg: null pointer");
+  DAMVS_REQUIRE(n_src >= 1 && n_src <= kMaxSrc, "warp_agg: n_src=%d outside [1,%d]", n_src, kMaxSrc);
+  DAMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "warp_agg: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+  DAMVS_REQUIRE(B <= 65535, "warp_agg: B too large");
+  DAMVS_REQUIRE(mode == DAMVS_AGG_VARIANCE || mode == DAMVS_AGG_ADAPTIVE, "warp_agg: bad mode %d", mode);
+  DAMVS_REQUIRE(mode == DAMVS_AGG_VARIANCE || wnet != nullptr, "warp_agg: adaptive mode needs wnet");
+  DAMVS_REQUIRE(out_dtype == DAMVS_F32 || out_dtype == DAMVS_BF16, "warp_agg: bad out_dtype %d", out_dtype);
+  DAMVS_REQUIRE(aligned16(ref_nhwc) && aligned16(out_vol), "warp_agg: ref/out must be 16-byte aligned");
+  WarpAggParams P;
+  P.ref = ref_nhwc;
+  for (int v = 0; v < kMaxSrc; ++v) P.src[v] = v < n_src ? src_nhwc[v] : nullptr;
+  for (int v = 0; v < n_src; ++v)
+    DAMVS_REQUIRE(src_nhwc[v] && aligned16(src_nhwc[v]), "warp_agg: src[%d] null or not 16-byte aligned", v);
+  P.rot_trans = rot_trans; P.hyp = depth_hyp; P.wnet = wnet; P.out = out_vol;
+  P.B = B; P.n_src = n_src; P.D = D; P.H = H; P.W = W; P.per_pixel = per_pixel_hyp;
+  cudaStream_t st = (cudaStream_t)stream;
+#define DISPATCH(CC)                                                                          \
+  case CC:                                                                                    \
+    return mode == DAMVS_AGG_ADAPTIVE ? launch_warp_agg<CC, DAMVS_AGG_ADAPTIVE>(P, out_dtype, st) \
+                                      : launch_warp_agg<CC, DAMVS_AGG_VARIANCE>(P, out_dtype, st);
+  switch (C) {
+    DISPATCH(8)
+    DISPATCH(16)
+    DISPATCH(32)
+    DISPATCH(64)
+    default:
+      return set_error(DAMVS_ERR_UNSUPPORTED, "warp_agg: C=%d not in {8,16,32,64}", C);
+  }
+#undef DISPATCH
+}
+
+extern "C" int damvs_homo_warp_fwd(const float* src_nhwc, const float* rot_trans, const float* depth_hyp,
+                                   float* out, int B, int C, int D, int H, int W, int per_pixel_hyp, void* stream) {
+  DAMVS_REQUIRE(src_nhwc && rot_trans && depth_hyp && out, "homo_warp: null pointer");
+  DAMVS_REQUIRE(B > 0 && C > 0 && C % 4 == 0 && D > 0 && H > 0 && W > 0, "homo_warp: bad shape (C must be a multiple of 4)");
+  DAMVS_REQUIRE(D <= 65535 && B <= 65535, "homo_warp: D or B too large");
+  DAMVS_REQUIRE(aligned16(src_nhwc), "homo_warp: src must be 16-byte aligned");
+  long long HW = (long long)H * W;
+  dim3 grid((unsigned)((HW + 255) / 256), D, B);
+  homo_warp_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src_nhwc, rot_trans, depth_hyp, out, C, D, H, W,
+                                                           per_pixel_hyp);
+  DAMVS_LAUNCH_OK("homo_warp kernel");
+  return DAMVS_OK;
+}

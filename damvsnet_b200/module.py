@@ -1,0 +1,248 @@
+"""Host-side mirror of the reference's ``models/module.py`` for the hot path.
+
+Same names, constructor arguments, parameter/buffer names (so reference
+checkpoints load with ``strict=True``) and call signatures as the reference:
+``Conv3d``, ``Deconv3d``, ``CostRegNet``, ``AggWeightNetVolume``,
+``homo_warping``, ``depth_regression``.  The arithmetic runs in the CUDA library
+behind include/damvs.h; parameters stay ordinary fp32 ``nn.Parameter``s in
+PyTorch layout and are repacked (BatchNorm folded, weights reordered / cast)
+into a per-module cache keyed on the parameters' version counters.
+
+Inference (``eval()``) is the native path.  Training-mode BatchNorm (batch
+statistics) is not implemented natively yet: modules raise in train mode rather
+than silently computing something else.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import G8Volume
+
+__all__ = ["Conv3d", "Deconv3d", "CostRegNet", "AggWeightNetVolume", "homo_warping", "depth_regression"]
+
+
+def _bn_affine(bn: nn.BatchNorm3d) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Eval-mode BatchNorm as (scale, shift) (reference models/module.py:141,150)."""
+    scale = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+    shift = bn.bias.detach() - bn.running_mean * scale
+    return scale.float().contiguous(), shift.float().contiguous()
+
+
+def _versions(*tensors) -> tuple:
+    return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+
+
+class _ConvBlock(nn.Module):
+    """Shared machinery of Conv3d / Deconv3d: parameters as in the reference, packed-weight cache."""
+
+    transposed = False
+
+    def _init_cache(self):
+        self._packed: Dict[tuple, tuple] = {}
+
+    def _train_guard(self):
+        if self.training and self.bn is not None:
+            raise NotImplementedError(
+                "damvsnet_b200: training-mode BatchNorm (batch statistics) has no native kernel yet; call .eval()")
+
+    def prepared(self, impl: int):
+        """(packed weight, scale, shift) for `impl` on the parameters' device, rebuilt when they change."""
+        w = self.conv.weight
+        bn = self.bn
+        key = (impl, w.device)
+        ver = _versions(w, *( (bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else () ))
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        cin, cout = self.in_channels, self.out_channels
+        packed = ops.conv3d_pack_weight(w.detach().float(), cin, cout, self.transposed, impl)
+        if bn is not None:
+            scale, shift = _bn_affine(bn)
+        elif self.conv.bias is not None:
+            scale = torch.ones(cout, dtype=torch.float32, device=w.device)
+            shift = self.conv.bias.detach().float().contiguous()
+        else:
+            scale = shift = None
+        val = (packed, scale, shift)
+        self._packed[key] = (ver, val)
+        return val
+
+    def forward_g8(self, vol: G8Volume, skip: Optional[G8Volume] = None, out_dtype: Optional[torch.dtype] = None) -> G8Volume:
+        """out = skip + relu(bn(conv(vol))) on G8 volumes (the path CostRegNet uses)."""
+        self._train_guard()
+        if self.kernel_size != 3:
+            raise NotImplementedError("native conv blocks are 3x3x3 only")
+        impl = ops.conv_impl_for(self.in_channels, self.out_channels, self.stride, self.transposed)
+        packed, scale, shift = self.prepared(impl)
+        return ops.conv3d(vol, packed, scale, shift, self.out_channels, self.stride, self.transposed, self.relu, skip,
+                          out_dtype or vol.dtype, False, impl)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Reference call signature: [B,C,D,H,W] fp32 in and out (repacked to/from G8 around the kernel)."""
+        if self.kernel_size != 3 or x.shape[1] % 8 or self.out_channels % 8 or self._padding != 1:
+            raise NotImplementedError(
+                "stand-alone Conv3d/Deconv3d forward is native for kernel 3, padding 1, channels % 8 == 0 only; "
+                "the 1x1x1 view-weight convs are fused into the warp/aggregate kernel (see DepthNet)")
+        vol = G8Volume.from_ncdhw(x, ops.volume_dtype())
+        return self.forward_g8(vol).to_ncdhw()
+
+
+class Conv3d(_ConvBlock):
+    """3-D convolution + BatchNorm + ReLU block (reference models/module.py:117-159)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, relu=True, bn=True, bn_momentum=0.1,
+                 init_method="xavier", **kwargs):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        assert stride in [1, 2]
+        self.stride = stride
+        self._padding = kwargs.get("padding", 0)
+        self.conv = nn.Conv3d(in_channels, out_channels, kernel_size, stride=stride, bias=(not bn), **kwargs)
+        self.bn = nn.BatchNorm3d(out_channels, momentum=bn_momentum) if bn else None
+        self.relu = relu
+        self._init_cache()
+
+
+class Deconv3d(_ConvBlock):
+    """3-D transposed convolution + BatchNorm + ReLU block (reference models/module.py:161-202)."""
+
+    transposed = True
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, relu=True, bn=True, bn_momentum=0.1,
+                 init_method="xavier", **kwargs):
+        super().__init__()
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = kernel_size
+        assert stride in [1, 2]
+        self.stride = stride
+        self._padding = kwargs.get("padding", 0)
+        if kernel_size == 3 and not (stride == 2 and kwargs.get("padding", 0) == 1 and kwargs.get("output_padding", 0) == 1):
+            raise NotImplementedError("native Deconv3d supports the reference's only configuration: k3, s2, p1, op1")
+        self.conv = nn.ConvTranspose3d(in_channels, out_channels, kernel_size, stride=stride, bias=(not bn), **kwargs)
+        self.bn = nn.BatchNorm3d(out_channels, momentum=bn_momentum) if bn else None
+        self.relu = relu
+        self._init_cache()
+
+
+class CostRegNet(nn.Module):
+    """3-level 3-D U-Net regulariser (reference models/module.py:510-541)."""
+
+    def __init__(self, in_channels, base_channels):
+        super().__init__()
+        self.conv0 = Conv3d(in_channels, base_channels, padding=1)
+        self.conv1 = Conv3d(base_channels, base_channels * 2, stride=2, padding=1)
+        self.conv2 = Conv3d(base_channels * 2, base_channels * 2, padding=1)
+        self.conv3 = Conv3d(base_channels * 2, base_channels * 4, stride=2, padding=1)
+        self.conv4 = Conv3d(base_channels * 4, base_channels * 4, padding=1)
+        self.conv5 = Conv3d(base_channels * 4, base_channels * 8, stride=2, padding=1)
+        self.conv6 = Conv3d(base_channels * 8, base_channels * 8, padding=1)
+        self.conv7 = Deconv3d(base_channels * 8, base_channels * 4, stride=2, padding=1, output_padding=1)
+        self.conv9 = Deconv3d(base_channels * 4, base_channels * 2, stride=2, padding=1, output_padding=1)
+        self.conv11 = Deconv3d(base_channels * 2, base_channels * 1, stride=2, padding=1, output_padding=1)
+        self.prob = nn.Conv3d(base_channels, 1, 3, stride=1, padding=1, bias=False)
+        self.in_channels = in_channels
+        self.base_channels = base_channels
+        self._prob_packed: Dict[tuple, tuple] = {}
+
+    def _prob_prepared(self, impl: int) -> torch.Tensor:
+        w = self.prob.weight
+        key = (impl, w.device)
+        ver = _versions(w)
+        hit = self._prob_packed.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        packed = ops.conv3d_pack_weight(w.detach().float(), self.base_channels, 1, False, impl)
+        self._prob_packed[key] = (ver, packed)
+        return packed
+
+    def forward_g8(self, vol: G8Volume) -> torch.Tensor:
+        """G8 cost volume -> logits [B,D,H,W] fp32 (the squeeze(1) of the reference output)."""
+        b, c, d, h, w = vol.shape
+        if c != self.in_channels:
+            raise ValueError(f"CostRegNet expects {self.in_channels} channels, got {c}")
+        if d % 8 or h % 8 or w % 8:
+            raise ValueError(f"CostRegNet needs D,H,W divisible by 8 (three stride-2 levels), got {(d, h, w)}")
+        conv0 = self.conv0.forward_g8(vol)
+        conv2 = self.conv2.forward_g8(self.conv1.forward_g8(conv0))
+        conv4 = self.conv4.forward_g8(self.conv3.forward_g8(conv2))
+        x = self.conv6.forward_g8(self.conv5.forward_g8(conv4))
+        x = self.conv7.forward_g8(x, skip=conv4)     # conv4 + conv7(x)
+        x = self.conv9.forward_g8(x, skip=conv2)
+        x = self.conv11.forward_g8(x, skip=conv0)
+        impl = ops.conv_impl_for(self.base_channels, 1, 1, False)
+        return ops.conv3d(x, self._prob_prepared(impl), None, None, 1, 1, False, False, None, torch.float32, True, impl)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Reference call signature: [B,C,D,H,W] -> [B,1,D,H,W]."""
+        vol = G8Volume.from_ncdhw(x, ops.volume_dtype())
+        return self.forward_g8(vol).unsqueeze(1)
+
+
+class AggWeightNetVolume(nn.Module):
+    """Per-view, per-voxel visibility weight net (reference models/module.py:544-563).
+
+    Parameters mirror the reference exactly, including the dead ``conv0``.  In
+    ``DepthNet`` the two 1x1x1 blocks are folded into five scalars plus a C-vector
+    (``folded()``) and evaluated inside the fused warp/aggregate kernel.
+    """
+
+    def __init__(self, in_channels=32):
+        super().__init__()
+        self.conv0 = Conv3d(in_channels, 1, kernel_size=1, stride=1, padding=0)
+        self.w_net = nn.Sequential(
+            Conv3d(in_channels, 1, kernel_size=1, stride=1, padding=0),
+            Conv3d(1, 1, kernel_size=1, stride=1, padding=0),
+        )
+        self.in_channels = in_channels
+        self._folded: Dict[torch.device, tuple] = {}
+
+    def folded(self) -> torch.Tensor:
+        """[C+5] fp32: w1[C], scale1, shift1, w2, scale2, shift2 (include/damvs.h, damvs_warp_agg_fwd)."""
+        a, b = self.w_net[0], self.w_net[1]
+        if self.training:
+            raise NotImplementedError(
+                "damvsnet_b200: training-mode view-weight BatchNorm has no native kernel yet; call .eval()")
+        tensors = (a.conv.weight, a.bn.weight, a.bn.bias, a.bn.running_mean, a.bn.running_var,
+                   b.conv.weight, b.bn.weight, b.bn.bias, b.bn.running_mean, b.bn.running_var)
+        ver = _versions(*tensors)
+        dev = a.conv.weight.device
+        hit = self._folded.get(dev)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        s1, b1 = _bn_affine(a.bn)
+        s2, b2 = _bn_affine(b.bn)
+        vec = torch.cat([a.conv.weight.detach().float().reshape(-1), s1, b1,
+                         b.conv.weight.detach().float().reshape(-1), s2, b2]).contiguous()
+        self._folded[dev] = (ver, vec)
+        return vec
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """Stand-alone reference signature [B,C,D,H,W] -> [B,1,D,H,W].  Not used by DepthNet (fused there);
+        evaluated with the same folded affine form the kernel uses."""
+        v = self.folded()
+        c = self.in_channels
+        s = (x * v[:c].view(1, c, 1, 1, 1)).sum(dim=1, keepdim=True)
+        a = torch.relu(s * v[c] + v[c + 1])
+        return torch.relu((a * v[c + 2]) * v[c + 3] + v[c + 4])
+
+
+def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.Tensor,
+                 depth_values: torch.Tensor) -> torch.Tensor:
+    """Reference signature (models/module.py:297-302): src_fea [B,C,H,W], src_proj/ref_proj [B,4,4],
+    depth_values [B,D] or [B,D,H,W] -> warped volume [B,C,D,H,W]."""
+    rot_trans = ops.relative_rot_trans(src_proj.float(), ref_proj.float())
+    return ops.homo_warp(ops.features_to_nhwc(src_fea), rot_trans, depth_values)
+
+
+def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tensor:
+    """Reference signature (models/module.py:609-615): sum_d p * depth_values."""
+    if depth_values.dim() == 1:
+        depth_values = depth_values.view(1, -1).expand(p.shape[0], -1)
+    return ops.depth_regression(p, depth_values.to(torch.float32))

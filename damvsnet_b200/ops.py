@@ -1,0 +1,356 @@
+"""Tensor-level wrappers over the C ABI (include/damvs.h).
+
+Everything here takes CUDA torch tensors, validates shape / dtype / contiguity,
+allocates outputs with torch (so the caching allocator owns all memory) and
+calls the library on torch's current stream.  PyTorch is plumbing only: device
+memory and streams.  There is no fallback path.
+"""
+from __future__ import annotations
+
+import contextlib
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import AGG_ADAPTIVE, AGG_VARIANCE, BF16, CONV_DIRECT, CONV_TCGEN05, F32, ConvDesc
+
+# --------------------------------------------------------------------------
+# precision policy
+# --------------------------------------------------------------------------
+_POLICY = {"precision": "bf16", "conv_impl": "auto"}
+
+
+def get_precision() -> str:
+    return _POLICY["precision"]
+
+
+def set_precision(precision: str, conv_impl: str = "auto") -> None:
+    """precision: 'bf16' (cost volume and CostRegNet activations in bf16, fp32 accumulate;
+    tensor-core convolutions) or 'fp32' (everything fp32, direct convolutions: the mode
+    the <=1e-4 depth parity claim is made in).  conv_impl: 'auto' | 'direct' | 'tcgen05'."""
+    assert precision in ("bf16", "fp32") and conv_impl in ("auto", "direct", "tcgen05")
+    _POLICY["precision"] = precision
+    _POLICY["conv_impl"] = conv_impl
+
+
+@contextlib.contextmanager
+def precision(precision: str, conv_impl: str = "auto"):
+    old = dict(_POLICY)
+    set_precision(precision, conv_impl)
+    try:
+        yield
+    finally:
+        _POLICY.update(old)
+
+
+def volume_dtype() -> torch.dtype:
+    return torch.bfloat16 if _POLICY["precision"] == "bf16" else torch.float32
+
+
+def conv_impl_for(cin: int, cout: int, stride: int, transposed: bool) -> int:
+    choice = _POLICY["conv_impl"]
+    if choice == "direct" or _POLICY["precision"] == "fp32":
+        return CONV_DIRECT
+    if choice == "tcgen05":
+        return CONV_TCGEN05
+    return CONV_TCGEN05 if tc_supported(cin, cout, stride, transposed) else CONV_DIRECT
+
+
+def tc_supported(cin: int, cout: int, stride: int, transposed: bool) -> bool:
+    """Layer shapes conv3d_tc.cu covers (bf16 in/out)."""
+    return False
+
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _need(t: torch.Tensor, name: str, dtype=torch.float32, ndim: Optional[int] = None) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise ValueError(f"{name}: expected a CUDA tensor (this package has no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got shape {tuple(t.shape)}")
+
+
+def _dt(dtype: torch.dtype) -> int:
+    return BF16 if dtype == torch.bfloat16 else F32
+
+
+@dataclass
+class G8Volume:
+    """A logical [B,C,D,H,W] volume stored as [B, C/8, D, H, W, 8] (include/damvs.h)."""
+    data: torch.Tensor
+
+    @property
+    def shape(self):
+        b, g, d, h, w, _ = self.data.shape
+        return (b, g * 8, d, h, w)
+
+    @property
+    def dtype(self):
+        return self.data.dtype
+
+    @staticmethod
+    def empty(b, c, d, h, w, dtype, device) -> "G8Volume":
+        assert c % 8 == 0
+        return G8Volume(torch.empty((b, c // 8, d, h, w, 8), dtype=dtype, device=device))
+
+    @staticmethod
+    def from_ncdhw(x: torch.Tensor, dtype: torch.dtype) -> "G8Volume":
+        _need(x, "x", torch.float32, 5)
+        x = x.contiguous()
+        b, c, d, h, w = x.shape
+        if c % 8:
+            raise ValueError(f"channel count {c} must be a multiple of 8")
+        out = G8Volume.empty(b, c, d, h, w, dtype, x.device)
+        with torch.cuda.device_of(x):
+            _lib.check(_lib.load().damvs_ncdhw_to_g8(_p(x), _p(out.data), _dt(dtype), b, c, d, h, w, _stream()))
+        return out
+
+    def to_ncdhw(self) -> torch.Tensor:
+        b, c, d, h, w = self.shape
+        out = torch.empty((b, c, d, h, w), dtype=torch.float32, device=self.data.device)
+        with torch.cuda.device_of(self.data):
+            _lib.check(_lib.load().damvs_g8_to_ncdhw(_p(self.data), _dt(self.dtype), _p(out), b, c, d, h, w, _stream()))
+        return out
+
+
+# --------------------------------------------------------------------------
+# features / projections
+# --------------------------------------------------------------------------
+def features_to_nhwc(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] fp32 -> contiguous [B,H,W,C].  Zero-copy when x is already channels_last."""
+    _need(x, "feature", torch.float32, 4)
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    x = x.contiguous()
+    b, c, h, w = x.shape
+    out = torch.empty((b, h, w, c), dtype=torch.float32, device=x.device)
+    with torch.cuda.device_of(x):
+        _lib.check(_lib.load().damvs_nchw_to_nhwc_f32(_p(x), _p(out), b, c, h, w, _stream()))
+    return out
+
+
+def compose_projection(proj_pair: torch.Tensor) -> torch.Tensor:
+    """[...,2,4,4] -> [...,4,4]: rows 0-2 = K @ E[:3,:4] (reference models/cas_mvsnet.py:44-47)."""
+    out = proj_pair[..., 0, :, :].clone()
+    out[..., :3, :4] = torch.matmul(proj_pair[..., 1, :3, :3], proj_pair[..., 0, :3, :4])
+    return out
+
+
+def relative_rot_trans(src_proj: torch.Tensor, ref_proj: torch.Tensor) -> torch.Tensor:
+    """[...,4,4] x [...,4,4] -> [...,12]: rows 0-2 of src_proj @ inverse(ref_proj), rot then trans
+    (reference models/module.py:308-310).  inv_ex avoids torch.inverse's host sync."""
+    inv = torch.linalg.inv_ex(ref_proj, check_errors=False).inverse
+    proj = torch.matmul(src_proj, inv)
+    return torch.cat([proj[..., :3, :3].reshape(*proj.shape[:-2], 9), proj[..., :3, 3]], dim=-1).contiguous()
+
+
+# --------------------------------------------------------------------------
+# kernels
+# --------------------------------------------------------------------------
+def _hyp_flags(depth_values: torch.Tensor, b: int, h: int, w: int):
+    _need(depth_values, "depth_values", torch.float32)
+    if depth_values.dim() == 2:
+        if depth_values.shape[0] != b:
+            raise ValueError("depth_values batch mismatch")
+        return depth_values.contiguous(), 0, depth_values.shape[1]
+    if depth_values.dim() == 4:
+        if depth_values.shape[0] != b or depth_values.shape[2] != h or depth_values.shape[3] != w:
+            raise ValueError(f"depth_values shape {tuple(depth_values.shape)} does not match [B={b},D,H={h},W={w}]")
+        return depth_values.contiguous(), 1, depth_values.shape[1]
+    raise ValueError("depth_values must be [B,D] or [B,D,H,W]")
+
+
+def homo_warp(src_nhwc: torch.Tensor, rot_trans: torch.Tensor, depth_values: torch.Tensor) -> torch.Tensor:
+    """Stand-alone warp: [B,H,W,C] -> [B,C,D,H,W] fp32 (reference models/module.py:297-332)."""
+    _need(src_nhwc, "src_nhwc", torch.float32, 4)
+    b, h, w, c = src_nhwc.shape
+    _need(rot_trans, "rot_trans", torch.float32, 2)
+    if tuple(rot_trans.shape) != (b, 12):
+        raise ValueError("rot_trans must be [B,12]")
+    dv, per_pixel, d = _hyp_flags(depth_values, b, h, w)
+    out = torch.empty((b, c, d, h, w), dtype=torch.float32, device=src_nhwc.device)
+    with torch.cuda.device_of(src_nhwc):
+        _lib.check(_lib.load().damvs_homo_warp_fwd(_p(src_nhwc.contiguous()), _p(rot_trans.contiguous()), _p(dv), _p(out),
+                                                   b, c, d, h, w, per_pixel, _stream()))
+    return out
+
+
+def warp_aggregate(ref_nhwc: torch.Tensor, src_nhwc: Sequence[torch.Tensor], rot_trans: torch.Tensor,
+                   depth_values: torch.Tensor, wnet: Optional[torch.Tensor], mode: str,
+                   out_dtype: torch.dtype) -> G8Volume:
+    """Fused warp + aggregation (reference models/cas_mvsnet.py:30-87) -> G8 cost volume."""
+    _need(ref_nhwc, "ref_nhwc", torch.float32, 4)
+    b, h, w, c = ref_nhwc.shape
+    n_src = len(src_nhwc)
+    for i, s in enumerate(src_nhwc):
+        _need(s, f"src_nhwc[{i}]", torch.float32, 4)
+        if s.shape != ref_nhwc.shape or not s.is_contiguous():
+            raise ValueError("source features must be contiguous and shaped like the reference feature")
+    _need(rot_trans, "rot_trans", torch.float32, 3)
+    if tuple(rot_trans.shape) != (n_src, b, 12):
+        raise ValueError(f"rot_trans must be [{n_src},{b},12], got {tuple(rot_trans.shape)}")
+    dv, per_pixel, d = _hyp_flags(depth_values, b, h, w)
+    if mode == "adaptive":
+        _need(wnet, "wnet", torch.float32, 1)
+        if wnet.numel() != c + 5:
+            raise ValueError("wnet must hold C+5 floats")
+        m = AGG_ADAPTIVE
+    elif mode == "variance":
+        m = AGG_VARIANCE
+        wnet = None
+    else:
+        raise ValueError(f"Don't support {mode}!")
+    out = G8Volume.empty(b, c, d, h, w, out_dtype, ref_nhwc.device)
+    ptrs = (ctypes.c_void_p * n_src)(*[s.data_ptr() for s in src_nhwc])
+    nbytes = (n_src + 1) * b * c * h * w * 4 + dv.numel() * 4 + out.data.numel() * out.data.element_size()
+    with torch.cuda.device_of(ref_nhwc), _timed("warp_agg", bytes=float(nbytes)):
+        _lib.check(_lib.load().damvs_warp_agg_fwd(_p(ref_nhwc.contiguous()), ptrs, n_src, _p(rot_trans.contiguous()), _p(dv),
+                                                  _p(wnet), _p(out.data), b, c, d, h, w, m, per_pixel, _dt(out_dtype),
+                                                  _stream()))
+    return out
+
+
+def conv_desc(b, cin, cout, din, hin, win, stride, transposed, relu, in_dtype, out_dtype, plain_out, impl) -> ConvDesc:
+    return ConvDesc(B=b, Cin=cin, Cout=cout, Din=din, Hin=hin, Win=win, stride=stride, transposed=int(transposed),
+                    relu=int(relu), in_dtype=_dt(in_dtype), out_dtype=_dt(out_dtype), plain_out=int(plain_out),
+                    impl=impl)
+
+
+def conv3d_pack_weight(weight: torch.Tensor, cin: int, cout: int, transposed: bool, impl: int) -> torch.Tensor:
+    """PyTorch-layout fp32 conv weight -> the packed buffer `impl` consumes (uint8 tensor)."""
+    _need(weight, "weight", torch.float32, 5)
+    desc = conv_desc(1, cin, cout, 1, 1, 1, 1, transposed, 0, torch.float32, torch.float32, cout == 1, impl)
+    lib = _lib.load()
+    nbytes = lib.damvs_conv3d_packed_weight_bytes(ctypes.byref(desc))
+    if nbytes == 0:
+        _lib.check(2)
+    packed = torch.empty(nbytes, dtype=torch.uint8, device=weight.device)
+    with torch.cuda.device_of(weight):
+        _lib.check(lib.damvs_conv3d_pack_weight(ctypes.byref(desc), _p(weight.detach().contiguous()), _p(packed), _stream()))
+    return packed
+
+
+def conv3d(vol: G8Volume, packed: torch.Tensor, scale: Optional[torch.Tensor], shift: Optional[torch.Tensor],
+           cout: int, stride: int, transposed: bool, relu: bool, skip: Optional[G8Volume], out_dtype: torch.dtype,
+           plain_out: bool, impl: int):
+    """One fused conv block: out = skip + act(conv(vol) * scale + shift)."""
+    b, cin, d, h, w = vol.shape
+    if transposed:
+        do, ho, wo = 2 * d, 2 * h, 2 * w
+    else:
+        do, ho, wo = (d - 1) // stride + 1, (h - 1) // stride + 1, (w - 1) // stride + 1
+    desc = conv_desc(b, cin, cout, d, h, w, stride, transposed, relu, vol.dtype, out_dtype, plain_out, impl)
+    dev = vol.data.device
+    if plain_out:
+        out_t = torch.empty((b, do, ho, wo), dtype=torch.float32, device=dev)
+        result = out_t
+    else:
+        result = G8Volume.empty(b, cout, do, ho, wo, out_dtype, dev)
+        out_t = result.data
+        if skip is not None and (skip.data.shape != out_t.shape or skip.dtype != out_dtype):
+            raise ValueError("skip volume must match the output volume")
+    vout = b * do * ho * wo
+    flops = 2.0 * 27 * cin * cout * (b * d * h * w if transposed else vout)
+    nbytes = vol.data.numel() * vol.data.element_size() + out_t.numel() * out_t.element_size() * (2 if skip is not None else 1)
+    tag = "conv3d_tc" if impl == CONV_TCGEN05 else "conv3d_direct"
+    with torch.cuda.device_of(vol.data), _timed(tag, bytes=float(nbytes), flops=flops):
+        _lib.check(_lib.load().damvs_conv3d_fwd(ctypes.byref(desc), _p(vol.data), _p(packed), _p(scale), _p(shift),
+                                                _p(None if skip is None else skip.data), _p(out_t), _stream()))
+    return result
+
+
+def softmax_regress(logits: torch.Tensor, depth_values: torch.Tensor, want_prob: bool = True):
+    """logits [B,D,H,W] -> (prob [B,D,H,W] | None, depth, confidence, variance [B,H,W])."""
+    _need(logits, "logits", torch.float32, 4)
+    logits = logits.contiguous()
+    b, d, h, w = logits.shape
+    dv, per_pixel, d2 = _hyp_flags(depth_values, b, h, w)
+    if d2 != d:
+        raise ValueError(f"depth_values.shape[1]:{d2}  num_depth:{d}")
+    dev = logits.device
+    prob = torch.empty_like(logits) if want_prob else None
+    depth = torch.empty((b, h, w), dtype=torch.float32, device=dev)
+    conf = torch.empty_like(depth)
+    var = torch.empty_like(depth)
+    nbytes = logits.numel() * 4 + dv.numel() * 4 + (logits.numel() * 4 if want_prob else 0) + 3 * b * h * w * 4
+    with torch.cuda.device_of(logits), _timed("head", bytes=float(nbytes)):
+        _lib.check(_lib.load().damvs_softmax_regress_fwd(_p(logits), _p(dv), _p(prob), _p(depth), _p(conf), _p(var),
+                                                         b, d, h, w, per_pixel, _stream()))
+    return prob, depth, conf, var
+
+
+def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tensor:
+    _need(p, "p", torch.float32, 4)
+    p = p.contiguous()
+    b, d, h, w = p.shape
+    dv, per_pixel, d2 = _hyp_flags(depth_values, b, h, w)
+    if d2 != d:
+        raise ValueError("depth_values / probability depth mismatch")
+    out = torch.empty((b, h, w), dtype=torch.float32, device=p.device)
+    with torch.cuda.device_of(p):
+        _lib.check(_lib.load().damvs_depth_regression_fwd(_p(p), _p(dv), _p(out), b, d, h, w, per_pixel, _stream()))
+    return out
+
+
+# --------------------------------------------------------------------------
+# per-call device timing (bench.py's roofline leg)
+# --------------------------------------------------------------------------
+class CallTimer:
+    """Records a CUDA-event pair around every library call made while active.
+
+    Events are recorded on torch's current stream, which is the stream the
+    kernels are launched on (``_stream()``), so the durations are device times.
+    """
+    active: Optional["CallTimer"] = None
+
+    def __init__(self):
+        self.records = []  # (tag, start_event, end_event, meta)
+
+    def __enter__(self):
+        CallTimer.active = self
+        return self
+
+    def __exit__(self, *exc):
+        CallTimer.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for tag, s, e, meta in self.records:
+            d = out.setdefault(tag, {"ms": 0.0, "calls": 0, "bytes": 0.0, "flops": 0.0})
+            d["ms"] += s.elapsed_time(e)
+            d["calls"] += 1
+            d["bytes"] += meta.get("bytes", 0.0)
+            d["flops"] += meta.get("flops", 0.0)
+        return out
+
+
+@contextlib.contextmanager
+def _timed(tag: str, **meta):
+    t = CallTimer.active
+    if t is None:
+        yield
+        return
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    try:
+        yield
+    finally:
+        e.record()
+        t.records.append((tag, s, e, meta))

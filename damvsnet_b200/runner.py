@@ -1,0 +1,121 @@
+"""Three-stage hot-path runner: the call a user of this package makes per reference view.
+
+``HotPathRunner`` owns one ``DepthNet`` and the per-stage ``CostRegNet``s (loaded from a
+reference-keyed state_dict) and exposes
+
+* ``run_device(stages)``  -- inputs already resident in HBM;
+* ``run_host(stages)``    -- inputs in (pinned) host memory: per view it uploads the
+  stage inputs on a copy stream, runs the three stages on the compute stream and
+  reads depth / confidence / variance back to pinned host buffers.  Uploads of
+  stage s+1 overlap the kernels of stage s.
+
+A "stage input" is ``(features: list of N [B,C,h,w] fp32, proj_matrices [B,N,2,4,4],
+depth_values [B,D,h,w])`` exactly as ``DepthNet.forward`` receives them in the
+reference (models/cas_mvsnet.py:292-298).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+
+from . import synthetic
+from .cas_mvsnet import DepthNet
+from .module import CostRegNet
+
+StageInput = Tuple[List[torch.Tensor], torch.Tensor, torch.Tensor]
+
+
+class HotPathRunner:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], mode: str = "adaptive",
+                 in_channels: Sequence[int] = synthetic.STAGE_CHANNELS, base_channels: Sequence[int] = (8, 8, 8),
+                 device: torch.device | str = "cuda:0"):
+        self.device = torch.device(device)
+        self.mode = mode
+        self.depthnet = DepthNet(mode, list(in_channels)).eval()
+        if mode == "adaptive":
+            self.depthnet.load_state_dict({k[len("DepthNet."):]: v for k, v in state_dict.items()
+                                           if k.startswith("DepthNet.")}, strict=True)
+        self.cost_regularization = torch.nn.ModuleList(
+            [CostRegNet(c, b) for c, b in zip(in_channels, base_channels)]).eval()
+        self.cost_regularization.load_state_dict({k[len("cost_regularization."):]: v for k, v in state_dict.items()
+                                                  if k.startswith("cost_regularization.")}, strict=True)
+        self.depthnet.to(self.device)
+        self.cost_regularization.to(self.device)
+        self._copy_stream = None
+        self._host_out = None
+
+    # ------------------------------------------------------------------ device-resident
+    @torch.no_grad()
+    def run_stage(self, stage_idx: int, features, proj, depth_values) -> Dict[str, torch.Tensor]:
+        return self.depthnet(stage_idx, features, proj, depth_values, depth_values.shape[1],
+                             self.cost_regularization[stage_idx])
+
+    @torch.no_grad()
+    def run_device(self, stages: Sequence[StageInput]) -> List[Dict[str, torch.Tensor]]:
+        return [self.run_stage(i, f, p, d) for i, (f, p, d) in enumerate(stages)]
+
+    # ------------------------------------------------------------------ host buffers
+    @staticmethod
+    def pin_stages(stages: Sequence[StageInput]) -> List[StageInput]:
+        return [([f.pin_memory() for f in feats], proj.pin_memory(), dv.pin_memory()) for feats, proj, dv in stages]
+
+    @staticmethod
+    def h2d_bytes(stages: Sequence[StageInput]) -> int:
+        n = 0
+        for feats, proj, dv in stages:
+            n += sum(f.numel() * f.element_size() for f in feats) + proj.numel() * 4 + dv.numel() * 4
+        return n
+
+    @staticmethod
+    def d2h_bytes(stages: Sequence[StageInput]) -> int:
+        return sum(3 * dv.shape[0] * dv.shape[2] * dv.shape[3] * 4 for _, _, dv in stages)
+
+    @torch.no_grad()
+    def run_host(self, stages: Sequence[StageInput]) -> List[Dict[str, torch.Tensor]]:
+        """Host tensors in, pinned host tensors (depth, photometric_confidence, variance per stage) out.
+        Returns after the results have landed on the host."""
+        dev = self.device
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        compute = torch.cuda.current_stream(dev)
+        copy = self._copy_stream
+        copy.wait_stream(compute)
+        uploaded, ready = [], []
+        with torch.cuda.stream(copy):
+            for feats, proj, dv in stages:
+                dfe = [f.to(dev, non_blocking=True) for f in feats]
+                dpr = proj.to(dev, non_blocking=True)
+                ddv = dv.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy)
+                uploaded.append((dfe, dpr, ddv))
+                ready.append(ev)
+        if self._host_out is None or len(self._host_out) != len(stages) or any(
+                o["depth"].shape != (dv.shape[0], dv.shape[2], dv.shape[3]) for o, (_, _, dv) in zip(self._host_out, stages)):
+            self._host_out = [{k: torch.empty((dv.shape[0], dv.shape[2], dv.shape[3]), dtype=torch.float32).pin_memory()
+                               for k in ("depth", "photometric_confidence", "variance")} for _, _, dv in stages]
+        outs = []
+        for i, ((dfe, dpr, ddv), ev) in enumerate(zip(uploaded, ready)):
+            compute.wait_event(ev)
+            for t in dfe + [dpr, ddv]:
+                t.record_stream(compute)
+            out = self.run_stage(i, dfe, dpr, ddv)
+            for k, host in self._host_out[i].items():
+                host.copy_(out[k], non_blocking=True)
+            outs.append(out)
+        compute.synchronize()
+        return self._host_out
+
+
+def make_workload(height: int, width: int, nviews: int, ndepths: Sequence[int], batch: int = 1, seed: int = 0,
+                  device: torch.device | str | None = None) -> List[StageInput]:
+    """Synthetic three-stage DepthNet inputs of the given image size."""
+    stages = []
+    for s, d in enumerate(ndepths):
+        feats, proj, dv = synthetic.make_stage_inputs(s, batch, nviews, height, width, d, seed=seed)
+        if device is not None:
+            feats = [f.to(device) for f in feats]
+            proj, dv = proj.to(device), dv.to(device)
+        stages.append((feats, proj, dv))
+    return stages

@@ -1,0 +1,141 @@
+/*
+ * damvs.h -- C ABI of the B200-native DA-MVSNet cost-volume hot path.
+ *
+ * One shared library (damvsnet_b200/_C/libdamvs_b200.so, sm_100a only).  Plain
+ * pointers and sizes, no torch types.  Every pointer marked "device" is a CUDA
+ * device pointer the caller owns for the duration of the call; the library never
+ * allocates, frees or retains device memory.  Every entry point is asynchronous
+ * on `stream` (a cudaStream_t passed as void*), performs no host synchronisation,
+ * returns 0 on success and a non-zero code otherwise (never throws, never exits);
+ * damvs_last_error() returns the message of the calling thread's last failure.
+ *
+ * The reference is pure Python (no FFI of its own), so each entry point cites the
+ * reference Python function whose arithmetic it replaces; INTEGRATION.md shows
+ * the ctypes binding a maintainer would add to the reference.
+ *
+ * Activation layout ("G8"): a logical [B,C,D,H,W] volume is stored as
+ * [B][C/8][D][H][W][8] -- eight channels innermost (16 B in bf16, 32 B in fp32),
+ * channel groups outermost, so that every 8-channel group is a dense D*H*W
+ * volume that TMA can tile with a contiguous inner dimension of W*8 elements.
+ * Feature maps are NHWC fp32: [B][H][W][C].
+ */
+#ifndef DAMVS_H_
+#define DAMVS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAMVS_ABI_VERSION 1
+
+enum damvs_status {
+  DAMVS_OK = 0,
+  DAMVS_ERR_INVALID = 1,     /* bad argument (shape, dtype, alignment, null) */
+  DAMVS_ERR_UNSUPPORTED = 2, /* valid request this build has no kernel for */
+  DAMVS_ERR_CUDA = 3,        /* CUDA runtime/driver error (message has cudaGetErrorString) */
+  DAMVS_ERR_NO_DEVICE = 4    /* device is not sm_100 */
+};
+
+enum damvs_dtype { DAMVS_F32 = 0, DAMVS_BF16 = 1 };
+enum damvs_agg_mode { DAMVS_AGG_VARIANCE = 0, DAMVS_AGG_ADAPTIVE = 1 };
+enum damvs_conv_impl { DAMVS_CONV_DIRECT = 0, DAMVS_CONV_TCGEN05 = 1 };
+
+int damvs_abi_version(void);
+const char* damvs_last_error(void);
+/* 0 when device `dev` can run this library (compute capability 10.x). */
+int damvs_check_device(int dev);
+
+/* ---- layout helpers ----------------------------------------------------- */
+/* [B,C,H,W] fp32 -> [B,H,W,C] fp32.  Feature maps handed over in the reference's
+ * NCHW layout (models/cas_mvsnet.py:24 `features`) are repacked once per view. */
+int damvs_nchw_to_nhwc_f32(const float* in, float* out, int B, int C, int H, int W, void* stream);
+/* [B,C,D,H,W] fp32 <-> G8 volume of `dtype`.  C % 8 == 0. */
+int damvs_ncdhw_to_g8(const float* in, void* out, int dtype, int B, int C, int D, int H, int W, void* stream);
+int damvs_g8_to_ncdhw(const void* in, int dtype, float* out, int B, int C, int D, int H, int W, void* stream);
+
+/* ---- homography warp (stand-alone) --------------------------------------- */
+/* Replaces homo_warping (reference models/module.py:297-332) from the sampling
+ * grid onwards; `rot_trans` holds, per batch item, rows 0-2 of
+ * src_proj @ inverse(ref_proj) as 12 floats (rot row-major, then trans), computed
+ * by the caller exactly as models/module.py:308-310 does.
+ *   src_nhwc   device [B,H,W,C] fp32
+ *   rot_trans  device [B,12] fp32
+ *   depth_hyp  device [B,D,H,W] (per_pixel_hyp=1) or [B,D] (per_pixel_hyp=0) fp32
+ *   out        device [B,C,D,H,W] fp32 (the reference's output layout)            */
+int damvs_homo_warp_fwd(const float* src_nhwc, const float* rot_trans, const float* depth_hyp, float* out,
+                        int B, int C, int D, int H, int W, int per_pixel_hyp, void* stream);
+
+/* ---- fused warp + multi-view aggregation --------------------------------- */
+/* Replaces the source-view loop of DepthNet.forward (reference
+ * models/cas_mvsnet.py:30-87): ref-volume repeat, homo_warping per source view,
+ * variance or adaptive aggregation including AggWeightNetVolume in eval mode
+ * (models/module.py:544-563).  The N x D warped volume never reaches memory.
+ *   ref_nhwc    device [B,H,W,C] fp32
+ *   src_nhwc    HOST array of n_src device pointers, each [B,H,W,C] fp32
+ *   rot_trans   device [n_src,B,12] fp32 (see damvs_homo_warp_fwd)
+ *   depth_hyp   device [B,D,H,W] or [B,D] fp32
+ *   wnet        device [C+5] fp32: w1[C], scale1, shift1, w2, scale2, shift2 -- the
+ *               two 1x1x1 convs of w_net and their folded eval-mode BatchNorms;
+ *               NULL for DAMVS_AGG_VARIANCE
+ *   out_vol     device G8 volume [B,C/8,D,H,W,8] of out_dtype
+ * C in {8,16,32,64}; n_src in [1,15].                                            */
+int damvs_warp_agg_fwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
+                       const float* depth_hyp, const float* wnet, void* out_vol, int B, int C, int D, int H,
+                       int W, int mode, int per_pixel_hyp, int out_dtype, void* stream);
+
+/* ---- 3-D convolution blocks of CostRegNet -------------------------------- */
+/* One Conv3d / Deconv3d block of the reference (models/module.py:117-202) with
+ * eval-mode BatchNorm folded to a per-channel affine, optional ReLU, and the
+ * additive U-Net skip of CostRegNet.forward (models/module.py:532-541) fused:
+ *     out = skip + act(conv(in) * scale + shift)
+ * kernel 3x3x3, padding 1; stride 1 or 2; transposed => ConvTranspose3d(k3, s2,
+ * p1, output_padding 1) whose output extent is twice the input's.               */
+typedef struct damvs_conv3d_desc {
+  int B, Cin, Cout;        /* Cin % 8 == 0; Cout % 8 == 0, or Cout == 1 with plain_out */
+  int Din, Hin, Win;       /* input extent */
+  int stride;              /* 1 or 2 (ignored when transposed) */
+  int transposed;          /* 0: Conv3d, 1: ConvTranspose3d(k3,s2,p1,op1) */
+  int relu;                /* apply ReLU after the affine */
+  int in_dtype, out_dtype; /* damvs_dtype of the G8 input / output volumes */
+  int plain_out;           /* 1: Cout == 1, output is plain fp32 [B,D,H,W] (the `prob` conv) */
+  int impl;                /* damvs_conv_impl */
+} damvs_conv3d_desc;
+
+/* Bytes of the packed weight buffer for (desc->impl, Cin, Cout). */
+size_t damvs_conv3d_packed_weight_bytes(const damvs_conv3d_desc* desc);
+/* Repack a PyTorch-layout fp32 weight (Conv3d: [Cout,Cin,3,3,3]; ConvTranspose3d:
+ * [Cin,Cout,3,3,3]; device pointer) into the layout `impl` consumes. */
+int damvs_conv3d_pack_weight(const damvs_conv3d_desc* desc, const float* weight, void* packed, void* stream);
+/*   in      device G8 volume [B,Cin/8,Din,Hin,Win,8]
+ *   packed  device, from damvs_conv3d_pack_weight
+ *   scale, shift  device [Cout] fp32, or NULL for identity (the `prob` conv has no BN)
+ *   skip    device, same layout/dtype as out, or NULL
+ *   out     device G8 volume of the output extent, or plain fp32 when plain_out  */
+int damvs_conv3d_fwd(const damvs_conv3d_desc* desc, const void* in, const void* packed, const float* scale,
+                     const float* shift, const void* skip, void* out, void* stream);
+
+/* ---- softmax / regression head -------------------------------------------- */
+/* Replaces models/cas_mvsnet.py:105-124 + depth_regression (models/module.py:609):
+ * softmax over D, expected depth, photometric confidence (sum of p over
+ * [idx-1, idx+2] at idx = trunc(sum p*k)), and 3*sqrt(sum p (d - depth)^2).
+ *   logits     device [B,D,H,W] fp32
+ *   depth_hyp  device [B,D,H,W] or [B,D] fp32
+ *   prob       device [B,D,H,W] fp32 out (may be NULL to skip the store)
+ *   depth, conf, var   device [B,H,W] fp32 out                                   */
+int damvs_softmax_regress_fwd(const float* logits, const float* depth_hyp, float* prob, float* depth,
+                              float* conf, float* var, int B, int D, int H, int W, int per_pixel_hyp,
+                              void* stream);
+/* depth_regression alone (models/module.py:609-615): out[b,h,w] = sum_d p * d. */
+int damvs_depth_regression_fwd(const float* prob, const float* depth_hyp, float* out, int B, int D, int H,
+                               int W, int per_pixel_hyp, void* stream);
+
+/* Number of kernel launches this library has issued in this process (for bench.py's gpu_launches). */
+uint64_t damvs_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAMVS_H_ */

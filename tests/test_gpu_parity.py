@@ -1,0 +1,272 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
+committed reference outputs.  Run on the B200 box with ``-m gpu``.
+
+Tolerances (north star): fp32 mode -- relative depth error <= 1e-4; bf16 mode
+(tensor-core convolutions, bf16 cost volume) -- teacher-forced per stage:
+depth rel p99 <= 1e-3, max <= 5e-3; confidence abs p99 <= 2e-3.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import damvs_oracle as O  # noqa: E402
+from tests import golden_io  # noqa: E402
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def dm():
+    import damvsnet_b200 as dm
+    from damvsnet_b200 import _lib
+    _lib.check(_lib.load().damvs_check_device(0))
+    return dm
+
+
+def _rel(a, b, floor=1.0):
+    return ((a - b).abs() / b.abs().clamp_min(floor))
+
+
+def _build_net(dm, sd, stage, mode):
+    from damvsnet_b200 import synthetic
+    cin = synthetic.STAGE_CHANNELS[stage]
+    net = dm.DepthNet(mode, list(synthetic.STAGE_CHANNELS)).eval()
+    cr = dm.CostRegNet(cin, 8).eval()
+    if mode == "adaptive":
+        net.load_state_dict({k[len("DepthNet."):]: v for k, v in sd.items() if k.startswith("DepthNet.")}, strict=True)
+    pre = f"cost_regularization.{stage}."
+    cr.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, strict=True)
+    return net.to(dev()), cr.to(dev())
+
+
+# ---------------------------------------------------------------- head
+@pytest.mark.parametrize("D", [8, 16, 32, 48, 64, 96])
+@pytest.mark.parametrize("per_pixel", [True, False])
+def test_head_matches_oracle(dm, D, per_pixel):
+    g = torch.Generator().manual_seed(D)
+    B, H, W = 2, 24, 40
+    logits = torch.randn(B, D, H, W, generator=g) * 3
+    hyp = 425 + 2.65 * torch.arange(D, dtype=torch.float32).view(1, D, 1, 1) + torch.rand(B, 1, H, W, generator=g)
+    hyp = hyp.expand(B, D, H, W).contiguous()
+    want = O.regress_head(logits, hyp)
+    dv = hyp if per_pixel else hyp[:, :, 0, 0].contiguous()
+    if not per_pixel:
+        want = O.regress_head(logits, dv.view(B, D, 1, 1).expand(B, D, H, W).contiguous())
+    prob, depth, conf, var = dm.ops.softmax_regress(logits.to(dev()), dv.to(dev()))
+    assert (prob.cpu() - want["prob_volume"]).abs().max() < 1e-6
+    assert _rel(depth.cpu(), want["depth"]).max() < 2e-6
+    assert ((conf.cpu() - want["photometric_confidence"]).abs() > 1e-5).float().mean() < 2e-3
+    assert _rel(var.cpu(), want["variance"], 1e-2).max() < 1e-3
+    assert (prob.sum(1) - 1).abs().max() < 1e-5
+
+
+def test_depth_regression_signature(dm):
+    g = golden_io.load_homo()
+    got4 = dm.depth_regression(g["p"].to(dev()), g["dv4"][:, :, :5, :7].contiguous().to(dev()))
+    got2 = dm.depth_regression(g["p"].to(dev()), g["dv2"].to(dev()))
+    torch.testing.assert_close(got4.cpu(), g["reg4"], rtol=1e-6, atol=1e-4)
+    torch.testing.assert_close(got2.cpu(), g["reg2"], rtol=1e-6, atol=1e-4)
+
+
+# ---------------------------------------------------------------- warp
+def test_homo_warping_matches_reference_fixture(dm):
+    g = golden_io.load_homo()
+    for dv, want in ((g["dv4"], g["out4"]), (g["dv2"], g["out2"])):
+        got = dm.homo_warping(g["src"].to(dev()), g["src_proj"].to(dev()), g["ref_proj"].to(dev()), dv.to(dev()))
+        assert got.shape == want.shape
+        assert (got.cpu() - want).abs().max() < 2e-4
+        assert (got.cpu() - want).abs().mean() < 2e-6
+
+
+def test_homo_warping_identity_is_identity(dm):
+    """Size-independent property: with src_proj == ref_proj the effective sample coordinate is
+    x*W/(W-1) - 0.5 (the reference's normalisation quirk), independent of depth."""
+    B, C, H, W, D = 1, 8, 33, 47, 3
+    src = torch.randn(B, C, H, W)
+    P = torch.eye(4).unsqueeze(0)
+    P[:, 0, 0] = 700.0
+    P[:, 1, 1] = 700.0
+    P[:, 0, 2] = 20.0
+    P[:, 1, 2] = 15.0
+    dv = torch.tensor([[400.0, 600.0, 900.0]])
+    got = dm.homo_warping(src.to(dev()), P.to(dev()), P.to(dev()), dv.to(dev())).cpu()
+    want = O.homo_warping(src, P, P, dv)
+    assert (got - want).abs().max() < 1e-4
+    assert (got[:, :, 0] - got[:, :, 2]).abs().max() < 1e-4
+
+
+# ---------------------------------------------------------------- layout
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_g8_round_trip(dm, dtype):
+    x = torch.randn(2, 16, 5, 9, 13)
+    if dtype == torch.bfloat16:
+        x = x.bfloat16().float()
+    vol = dm.G8Volume.from_ncdhw(x.to(dev()), dtype)
+    assert vol.data.shape == (2, 2, 5, 9, 13, 8)
+    ref = x.view(2, 2, 8, 5, 9, 13).permute(0, 1, 3, 4, 5, 2)
+    assert torch.equal(vol.data.float().cpu(), ref)
+    assert torch.equal(vol.to_ncdhw().cpu(), x)
+
+
+def test_nhwc_repack_and_zero_copy(dm):
+    x = torch.randn(2, 32, 19, 23, device=dev())
+    y = dm.ops.features_to_nhwc(x)
+    assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
+    xc = x.contiguous(memory_format=torch.channels_last)
+    yc = dm.ops.features_to_nhwc(xc)
+    assert yc.data_ptr() == xc.data_ptr() and torch.equal(yc, y)
+
+
+# ---------------------------------------------------------------- aggregate
+@pytest.mark.parametrize("mode", ["adaptive", "variance"])
+@pytest.mark.parametrize("stage", [0, 1, 2])
+def test_cost_volume_matches_reference_fixture(dm, mode, stage):
+    sd, stages = golden_io.load_depthnet(mode)
+    st = stages[stage]
+    net, _ = _build_net(dm, sd, stage, mode)
+    vol = net.cost_volume(stage, [f.to(dev()) for f in st["features"]], st["proj"].to(dev()),
+                          st["depth_values"].to(dev()), out_dtype=torch.float32)
+    got = vol.to_ncdhw().cpu()[:, :, ::2, ::3, ::3]
+    scale = max(st["volume_sub"].abs().mean().item(), 1.0)
+    assert (got - st["volume_sub"]).abs().max() < 2e-3 * scale
+    assert (got - st["volume_sub"]).abs().mean() < 1e-5 * scale
+
+
+@pytest.mark.parametrize("mode", ["adaptive", "variance"])
+@pytest.mark.parametrize("C", [8, 16, 32])
+def test_cost_volume_matches_oracle_ragged(dm, mode, C):
+    """Ragged extents (not multiples of the CTA tile), 2 batch items, [B,D] and [B,D,H,W] hypotheses."""
+    from damvsnet_b200 import synthetic
+    stage = {32: 0, 16: 1, 8: 2}[C]
+    sd = synthetic.hot_path_state_dict(seed=11)
+    feats, pm, dv = synthetic.make_stage_inputs(stage, 2, 3, 4 * 37, 4 * 45, 5, seed=4, channels=C)
+    feats = [f[:, :, :37, :45].contiguous() for f in feats]
+    dv = dv[:, :, :37, :45].contiguous()
+    net, _ = _build_net(dm, sd, stage, mode)
+    for hyp in (dv, dv[:, :, 0, 0].contiguous()):
+        want = O.aggregate(feats, pm, hyp, mode, sd, stage)
+        got = net.cost_volume(stage, [f.to(dev()) for f in feats], pm.to(dev()), hyp.to(dev()),
+                              out_dtype=torch.float32).to_ncdhw().cpu()
+        scale = max(want.abs().mean().item(), 1.0)
+        assert (got - want).abs().max() < 2e-3 * scale
+        assert (got - want).abs().mean() < 1e-5 * scale
+    bf = net.cost_volume(stage, [f.to(dev()) for f in feats], pm.to(dev()), dv.to(dev()),
+                         out_dtype=torch.bfloat16).to_ncdhw().cpu()
+    want = O.aggregate(feats, pm, dv, mode, sd, stage)
+    assert ((bf - want).abs() <= want.abs() * 2 ** -7 + 2e-3).all()
+
+
+def test_variance_of_identical_views_is_zero_full_size(dm):
+    """Size-independent property at the BASELINE stage-1 extent: identical views under identity
+    relative pose sample themselves (up to the W/(W-1) quirk) -- use a constant feature so the
+    variance must vanish exactly, and the adaptive cost must be exactly zero."""
+    B, C, D, H, W = 1, 32, 48, 288, 400
+    f = torch.full((B, C, H, W), 0.75, device=dev())
+    pm = torch.zeros(B, 3, 2, 4, 4)
+    pm[:, :, 0] = torch.eye(4)
+    pm[:, :, 1, :3, :3] = torch.tensor([[720.0, 0, 199.5], [0, 720.0, 143.5], [0, 0, 1]])
+    dv = (425 + 10.0 * torch.arange(D, dtype=torch.float32)).view(1, D).to(dev())
+    net = dm.DepthNet("variance", [32, 16, 8]).eval().to(dev())
+    vol = net.cost_volume(0, [f, f, f], pm.to(dev()), dv, out_dtype=torch.float32).data
+    inner = vol[:, :, :, 2:-2, 2:-2]
+    assert inner.abs().max().item() < 1e-6
+
+
+# ---------------------------------------------------------------- conv blocks
+def _rand_bn(bn, g):
+    with torch.no_grad():
+        bn.weight.copy_(0.8 + 0.4 * torch.rand(bn.weight.shape, generator=g))
+        bn.bias.copy_(0.1 * torch.randn(bn.bias.shape, generator=g))
+        bn.running_mean.copy_(0.05 * torch.randn(bn.bias.shape, generator=g))
+        bn.running_var.copy_(0.5 + torch.rand(bn.bias.shape, generator=g))
+
+
+@pytest.mark.parametrize("cin,cout,stride,transposed", [
+    (8, 8, 1, False), (32, 8, 1, False), (8, 16, 2, False), (16, 32, 2, False), (64, 64, 1, False),
+    (64, 32, 1, True), (16, 8, 1, True)])
+def test_conv_block_fp32_matches_torch(dm, cin, cout, stride, transposed):
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    if transposed:
+        blk = dm.Deconv3d(cin, cout, stride=2, padding=1, output_padding=1)
+    else:
+        blk = dm.Conv3d(cin, cout, stride=stride, padding=1)
+    _rand_bn(blk.bn, g)
+    blk = blk.eval()
+    x = torch.randn(2, cin, 6, 10, 14, generator=g)
+    with torch.no_grad():
+        want = torch.relu(blk.bn(blk.conv(x)))
+    skip = torch.randn(want.shape, generator=g)
+    blk = blk.to(dev())
+    with dm.precision("fp32"):
+        got = blk(x.to(dev())).cpu()
+        vol = dm.G8Volume.from_ncdhw(x.to(dev()), torch.float32)
+        sk = dm.G8Volume.from_ncdhw(skip.to(dev()), torch.float32)
+        got_skip = blk.forward_g8(vol, skip=sk).to_ncdhw().cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max() < 2e-5 * max(1.0, want.abs().max().item())
+    assert (got_skip - (want + skip)).abs().max() < 2e-5 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2])
+def test_cost_reg_net_fp32_matches_oracle(dm, stage):
+    from damvsnet_b200 import synthetic
+    sd = synthetic.hot_path_state_dict(seed=2)
+    cin = synthetic.STAGE_CHANNELS[stage]
+    _, cr = _build_net(dm, sd, stage, "variance")
+    x = torch.rand(1, cin, 8, 16, 24) * 0.5
+    want = O.cost_reg_net(x, sd, stage)
+    with dm.precision("fp32"):
+        got = cr(x.to(dev())).cpu()
+    assert got.shape == want.shape == (1, 1, 8, 16, 24)
+    assert (got - want).abs().max() < 1e-4 * max(1.0, want.abs().max().item())
+
+
+def test_cost_reg_net_rejects_bad_extent(dm):
+    cr = dm.CostRegNet(8, 8).eval().to(dev())
+    with pytest.raises(ValueError):
+        cr(torch.zeros(1, 8, 8, 12, 16, device=dev()))
+    with pytest.raises(ValueError):
+        dm.ops.softmax_regress(torch.zeros(1, 4, 4, 4), torch.zeros(1, 4, 4, 4))  # CPU tensors: no CPU path
+
+
+# ---------------------------------------------------------------- whole stage
+def _check_stage(out, st, depth_max, depth_p99, conf_tol, conf_frac):
+    rel = _rel(out["depth"].cpu(), st["depth"])
+    assert rel.max().item() < depth_max, rel.max().item()
+    assert torch.quantile(rel.flatten(), 0.99).item() < depth_p99
+    bad = ((out["photometric_confidence"].cpu() - st["photometric_confidence"]).abs() > conf_tol).float().mean().item()
+    assert bad <= conf_frac, bad
+    assert set(out) == {"depth", "photometric_confidence", "variance", "prob_volume", "depth_values"}
+    assert out["prob_volume"].shape == st["prob_volume"].shape and out["depth"].shape == st["depth"].shape
+
+
+@pytest.mark.parametrize("mode", ["adaptive", "variance"])
+@pytest.mark.parametrize("stage", [0, 1, 2])
+def test_depthnet_fp32_matches_reference_fixture(dm, mode, stage):
+    """The headline parity claim: fp32 path, relative depth error <= 1e-4 against the reference's outputs."""
+    sd, stages = golden_io.load_depthnet(mode)
+    st = stages[stage]
+    net, cr = _build_net(dm, sd, stage, mode)
+    with dm.precision("fp32"), torch.no_grad():
+        out = net(stage, [f.to(dev()) for f in st["features"]], st["proj"].to(dev()), st["depth_values"].to(dev()),
+                  st["depth_values"].shape[1], cr)
+    _check_stage(out, st, depth_max=1e-4, depth_p99=2e-5, conf_tol=2e-3, conf_frac=2e-3)
+    assert (out["prob_volume"].cpu() - st["prob_volume"]).abs().max() < 2e-3
+    vrel = _rel(out["variance"].cpu(), st["variance"], 1e-2)
+    assert torch.quantile(vrel.flatten(), 0.99).item() < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["adaptive", "variance"])
+@pytest.mark.parametrize("stage", [0, 1, 2])
+def test_depthnet_bf16_within_stated_bound(dm, mode, stage):
+    """bf16 cost volume + bf16 conv activations (fp32 accumulate): the stated bf16 bound, teacher-forced per stage."""
+    sd, stages = golden_io.load_depthnet(mode)
+    st = stages[stage]
+    net, cr = _build_net(dm, sd, stage, mode)
+    with dm.precision("bf16"), torch.no_grad():
+        out = net(stage, [f.to(dev()) for f in st["features"]], st["proj"].to(dev()), st["depth_values"].to(dev()),
+                  st["depth_values"].shape[1], cr)
+    _check_stage(out, st, depth_max=2e-2, depth_p99=5e-3, conf_tol=5e-2, conf_frac=2e-2)
