@@ -1,15 +1,564 @@
-// tcgen05 / TMEM implicit-GEMM 3x3x3 convolution (placeholder until the kernel lands).
+// tcgen05 / TMEM implicit-GEMM 3x3x3 convolution blocks of CostRegNet (bf16 in, fp32 accumulate).
+//
+// Replaces Conv3d / Deconv3d (reference models/module.py:117-202: nn.Conv3d /
+// nn.ConvTranspose3d + BatchNorm3d + ReLU) and the skip-adds of CostRegNet.forward
+// (models/module.py:532-541) with one kernel per layer:
+//     out = skip + relu((conv(in)) * scale + shift)
+//
+// GEMM view: M = output voxels, N = Cout (padded to a multiple of 16), K = 27 * Cin.
+// The A operand is never materialised (no im2col):
+//   * activations live in the G8 layout ([B][C/8][D][H][W][8] bf16), so an 8-channel group of a
+//     (rows x 32 voxels) patch of one depth plane lands in shared memory, via ONE TMA box load with
+//     a contiguous 512-byte inner dimension, as a dense array of 16-byte rows -- exactly the
+//     no-swizzle K-major UMMA layout (8-row x 16-byte core matrices, SBO = 128 B);
+//   * GEMM row m = ty*32 + tx of a tile; a filter tap (kh, kw) is the SAME shared-memory patch
+//     shifted by kh*32 + kw rows, i.e. just a different descriptor start address; the two 8-channel
+//     K-halves of one K=16 MMA are two such addresses LBO bytes apart (the next channel group's
+//     plane, or -- for Cin = 8 -- the next tap);
+//   * depth taps come from a ring of plane slots that slides along D, so every input plane is
+//     loaded once per CTA; out-of-range planes / rows / columns are TMA zero fill (= padding 1).
+// Columns tx >= tile width of every row are garbage GEMM rows that are computed and dropped.
+//
+// Three modes share the kernel: stride-1 conv, stride-2 conv (even/odd input rows as two patches;
+// odd output columns computed and dropped) and the k3/s2/p1/op1 transposed conv (8 output-parity
+// classes, each a 1/2/4/8-tap sub-convolution of the same input patch, own TMEM accumulator).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
+// epilogue (TMEM -> registers -> BN affine / ReLU / skip -> 16-byte stores).  Accumulators are
+// double buffered in TMEM so the epilogue of plane z overlaps the MMAs of plane z+1.
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace damvs {
 
-int conv3d_tc_launch(const damvs_conv3d_desc*, const void*, const void*, const float*, const float*, const void*,
-                     void*, cudaStream_t) {
-  return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d: tcgen05 implementation not built yet");
+using namespace tc;
+
+constexpr int kP = 32;       // patch pitch in voxels (one TMA box row = 32 voxels * 16 B)
+constexpr int kSlots = 4;    // depth-plane ring
+constexpr int kMaxSteps = 128;
+constexpr uint32_t kMagic = 0x44544331u;  // "DTC1"
+
+enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T = 2 };
+
+// One K=16 MMA of the per-iteration program, in layer-independent form (host-built, stored in the packed buffer).
+struct StepSrc {
+  int8_t slot_rel, cls, first, pad_;
+  int8_t patch[2], g[2], dy[2], dx[2], tap[2];  // per K-half; tap < 0 => zero weights
+};
+struct PackedHeader {  // 64 bytes
+  uint32_t magic;
+  int32_t mode, Cin, Cout, N, nsteps, ncls, n0;  // n0: first output channel this blob computes
+  int32_t blob_bytes, nblobs, pad[6];
+};
+struct StepRt {
+  uint32_t a_off;  // bytes from the slot base
+  uint16_t lbo;    // bytes
+  uint8_t slot_rel, cls_first;  // bit 7: first
+};
+
+struct TcParams {
+  const uint8_t* blob;  // PackedHeader + StepSrc[nsteps] (padded to 16 B) + weights
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* skip;
+  void* out;
+  int B, G, Din, Hin, Win, Dout, Hout, Wout;
+  int out_G, out_g0;  // output volume's group count and first group written by this launch
+  int n0, Cout, relu, plain_out, niter;
+};
+
+__host__ __device__ inline int steps_offset() { return (int)sizeof(PackedHeader); }
+__host__ __device__ inline int weights_offset(int nsteps) { return (int)sizeof(PackedHeader) + ((nsteps * (int)sizeof(StepSrc) + 15) & ~15); }
+
+template <int MODE>
+struct Geo {
+  static constexpr int span = MODE == MODE_T ? 2 : 3;
+  static constexpr int adv = MODE == MODE_S2 ? 2 : 1;
+  static constexpr int p0 = MODE == MODE_T ? 0 : -1;
+  static constexpr int ncls = MODE == MODE_T ? 8 : 1;
+  static constexpr int TW = MODE == MODE_S1 ? 30 : (MODE == MODE_T ? 31 : 15);
+  __host__ __device__ static constexpr int rows0(int MC) { return MODE == MODE_S1 ? 4 * MC + 2 : (MODE == MODE_T ? 4 * MC + 1 : 4 * MC); }
+  __host__ __device__ static constexpr int rows1(int MC) { return MODE == MODE_S2 ? 4 * MC + 1 : 0; }
+};
+
+template <int MODE, int N, int MC>
+__global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0,
+                                                        const __grid_constant__ CUtensorMap map1, const TcParams P) {
+  using G_ = Geo<MODE>;
+  constexpr int TH = 4 * MC;
+  constexpr int ACC_COLS = G_::ncls * MC * N;
+  constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
+  static_assert(2 * ACC_COLS <= 512, "TMEM budget");
+  constexpr uint32_t IDESC = idesc_bf16_m128(N);
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int G = P.G;
+  const int patch0_bytes = G * G_::rows0(MC) * kP * 16;
+  const int patch1_bytes = G * G_::rows1(MC) * kP * 16;
+  const int slot_stride = patch0_bytes + patch1_bytes + 128;
+  const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(P.blob);
+  const int nsteps = hdr->nsteps;
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + kSlots * slot_stride;
+  StepRt* sProg = reinterpret_cast<StepRt*>(sB + nsteps * 2 * N * 16);
+  float* sScale = reinterpret_cast<float*>(sProg + kMaxSteps);
+  float* sShift = sScale + N;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + N);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kSlots;
+  uint64_t* tmem_full = bars + 2 * kSlots;
+  uint64_t* tmem_empty = bars + 2 * kSlots + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z;
+  const int ty0 = blockIdx.y * TH;     // tile origin (output coords for S1/S2, input coords for T)
+  const int tx0 = blockIdx.x * G_::TW;
+
+  // ---- one-time setup ------------------------------------------------------------------------
+  {
+    const uint4* wsrc = reinterpret_cast<const uint4*>(P.blob + weights_offset(nsteps));
+    uint4* wdst = reinterpret_cast<uint4*>(sB);
+    for (int i = threadIdx.x; i < nsteps * 2 * N; i += blockDim.x) wdst[i] = __ldg(wsrc + i);
+    const StepSrc* src = reinterpret_cast<const StepSrc*>(P.blob + steps_offset());
+    for (int s = threadIdx.x; s < nsteps; s += blockDim.x) {
+      StepSrc st = src[s];
+      uint32_t off[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        int rows = st.patch[h] ? G_::rows1(MC) : G_::rows0(MC);
+        off[h] = (st.patch[h] ? patch0_bytes : 0) + ((st.g[h] * rows + st.dy[h]) * kP + st.dx[h]) * 16;
+      }
+      StepRt rt;
+      rt.a_off = off[0];
+      rt.lbo = (uint16_t)(off[1] - off[0]);
+      rt.slot_rel = (uint8_t)st.slot_rel;
+      rt.cls_first = (uint8_t)(st.cls | (st.first ? 0x80 : 0));
+      sProg[s] = rt;
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      int co = P.n0 + i;
+      bool ok = co < P.Cout;
+      sScale[i] = ok ? (P.scale ? __ldg(P.scale + co) : 1.f) : 0.f;
+      sShift[i] = ok && P.shift ? __ldg(P.shift + co) : 0.f;
+    }
+    // the 128-byte tail of every slot is read by the last (discarded) GEMM rows: keep it finite
+    for (int i = threadIdx.x; i < kSlots * 32; i += blockDim.x)
+      reinterpret_cast<uint32_t*>(sA + (i / 32) * slot_stride + patch0_bytes + patch1_bytes)[i % 32] = 0u;
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);
+    fence_barrier_init();
+    tma_prefetch_desc(&map0);
+    if (MODE == MODE_S2) tma_prefetch_desc(&map1);
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
+  fence_proxy_async();  // generic-proxy smem writes (weights, pad) -> visible to the async proxy (UMMA)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int niter = P.niter;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const int nplanes = (niter - 1) * G_::adv + G_::span;
+      const uint32_t bytes = (uint32_t)(patch0_bytes + patch1_bytes);
+      for (int k = 0; k < nplanes; ++k) {
+        const int slot = k % kSlots;
+        if (k >= kSlots) mbar_wait(&empty[slot], ((k / kSlots) - 1) & 1);
+        mbar_arrive_expect_tx(&full[slot], bytes);
+        uint8_t* dst = sA + slot * slot_stride;
+        const int plane = k + G_::p0;
+        if (MODE == MODE_S1) {
+          tma_load_4d(dst, &map0, &full[slot], (tx0 - 1) * 8, ty0 - 1, plane, b * G);
+        } else if (MODE == MODE_T) {
+          tma_load_4d(dst, &map0, &full[slot], tx0 * 8, ty0, plane, b * G);
+        } else {
+          tma_load_4d(dst, &map0, &full[slot], (2 * tx0 - 1) * 8, ty0, plane, b * G);                    // even rows 2*(ty0+r)
+          tma_load_4d(dst + patch0_bytes, &map1, &full[slot], (2 * tx0 - 1) * 8, ty0 - 1, plane, b * G);  // odd rows 2*(ty0+r)-1
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
+      int next_wait = 0;
+      for (int it = 0; it < niter; ++it) {
+        const int need = it * G_::adv + G_::span - 1;
+        while (next_wait <= need) {
+          mbar_wait(&full[next_wait % kSlots], (next_wait / kSlots) & 1);
+          ++next_wait;
+        }
+        const int buf = it & 1;
+        if (it >= 2) mbar_wait(&tmem_empty[buf], ((it >> 1) - 1) & 1);
+        tc_fence_after();
+        const uint32_t dbase = tmem_base + buf * ACC_COLS;
+        for (int s = 0; s < nsteps; ++s) {
+          const StepRt st = sProg[s];
+          const int slot = (it * G_::adv + st.slot_rel) % kSlots;
+          const uint32_t a_addr = a_base + slot * slot_stride + st.a_off;
+          const uint64_t bdesc = smem_desc(b_base + s * (2 * N * 16), N * 16, 128);
+          const uint32_t cls = st.cls_first & 0x7f, acc = (st.cls_first & 0x80) ? 0u : 1u;
+#pragma unroll
+          for (int c = 0; c < MC; ++c) {
+            const uint64_t adesc = smem_desc(a_addr + c * 128 * 16, st.lbo, 128);
+            mma_bf16_ss(dbase + (cls * MC + c) * N, adesc, bdesc, IDESC, acc);
+          }
+        }
+        mma_commit(&tmem_full[buf]);
+#pragma unroll
+        for (int a = 0; a < G_::adv; ++a) mma_commit(&empty[(it * G_::adv + a) % kSlots]);
+      }
+    }
+  } else {
+    // ===== epilogue: 4 warps, warp q owns TMEM lanes 32q..32q+31 =====
+    const int q = warp & 3;
+    const int Gout_local = N / 8;
+    const long long HWo = (long long)P.Hout * P.Wout;
+    for (int it = 0; it < niter; ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS;
+#pragma unroll
+      for (int c = 0; c < MC; ++c) {
+        const int ty = c * 4 + q, tx = lane;
+        if (MODE == MODE_T) {
+          const int yi = ty0 + ty, xi = tx0 + tx;
+          const bool valid = tx < G_::TW && yi < P.Hin && xi < P.Win;
+#pragma unroll 1
+          for (int pdh = 0; pdh < 4; ++pdh) {
+            const int pd = pdh >> 1, ph = pdh & 1;
+            const int zo = 2 * it + pd, yo = 2 * yi + ph, xo = 2 * xi;
+#pragma unroll
+            for (int n0 = 0; n0 < N; n0 += 8) {
+              uint32_t v0[8], v1[8];
+              tmem_ld8(tbase + ((pdh * 2 + 0) * MC + c) * N + n0, v0);
+              tmem_ld8(tbase + ((pdh * 2 + 1) * MC + c) * N + n0, v1);
+              tmem_ld_wait();
+              if (valid && P.n0 + n0 < P.Cout) {
+                const int go = P.out_g0 + n0 / 8;
+                const size_t off = g8_offset(b, go, zo, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
+                F8 r0, r1;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float a = __uint_as_float(v0[j]) * sScale[n0 + j] + sShift[n0 + j];
+                  float bb = __uint_as_float(v1[j]) * sScale[n0 + j] + sShift[n0 + j];
+                  if (P.relu) { a = fmaxf(a, 0.f); bb = fmaxf(bb, 0.f); }
+                  r0.v[j] = a; r1.v[j] = bb;
+                }
+                if (P.skip) {
+                  F8 s0 = load8(P.skip + off), s1 = load8(P.skip + off + 8);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) { r0.v[j] += s0.v[j]; r1.v[j] += s1.v[j]; }
+                }
+                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + off;
+                store8(o, r0);
+                store8(o + 8, r1);
+              }
+            }
+          }
+        } else {
+          int yo, xo;
+          bool valid;
+          if (MODE == MODE_S1) {
+            yo = ty0 + ty; xo = tx0 + tx;
+            valid = tx < G_::TW && yo < P.Hout && xo < P.Wout;
+          } else {
+            yo = ty0 + ty; xo = tx0 + (tx >> 1);
+            valid = !(tx & 1) && (tx >> 1) < G_::TW && yo < P.Hout && xo < P.Wout;
+          }
+          if (P.plain_out) {
+            uint32_t v[8];
+            tmem_ld8(tbase + c * N, v);
+            tmem_ld_wait();
+            if (valid) reinterpret_cast<float*>(P.out)[((long long)b * P.Dout + it) * HWo + (long long)yo * P.Wout + xo] = __uint_as_float(v[0]);
+          } else {
+#pragma unroll
+            for (int n0 = 0; n0 < N; n0 += 8) {
+              uint32_t v[8];
+              tmem_ld8(tbase + c * N + n0, v);
+              tmem_ld_wait();
+              if (valid && P.n0 + n0 < P.Cout) {
+                const int go = P.out_g0 + n0 / 8;
+                const size_t off = g8_offset(b, go, it, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
+                F8 r;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float a = __uint_as_float(v[j]) * sScale[n0 + j] + sShift[n0 + j];
+                  r.v[j] = P.relu ? fmaxf(a, 0.f) : a;
+                }
+                if (P.skip) {
+                  F8 s = load8(P.skip + off);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) r.v[j] += s.v[j];
+                }
+                store8(reinterpret_cast<__nv_bfloat16*>(P.out) + off, r);
+              }
+            }
+          }
+        }
+      }
+      (void)Gout_local;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
-size_t conv3d_tc_packed_bytes(const damvs_conv3d_desc*) { return 0; }
-int conv3d_tc_pack(const damvs_conv3d_desc*, const float*, void*, cudaStream_t) {
-  return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d: tcgen05 implementation not built yet");
+
+// ---------------------------------------------------------------------------------------------
+// host side: per-layer MMA program, weight packing, tensor maps, launch
+// ---------------------------------------------------------------------------------------------
+static int mode_of(const damvs_conv3d_desc* d) { return d->transposed ? MODE_T : (d->stride == 2 ? MODE_S2 : MODE_S1); }
+static int padded_n(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
+
+struct Half { int patch, g, dy, dx, tap; };
+
+static bool build_program(int mode, int G, std::vector<StepSrc>& steps) {
+  steps.clear();
+  auto emit = [&](int slot_rel, int cls, bool first, const Half& a, const Half& b2) {
+    StepSrc s{};
+    s.slot_rel = (int8_t)slot_rel; s.cls = (int8_t)cls; s.first = first ? 1 : 0;
+    const Half* h[2] = {&a, &b2};
+    for (int i = 0; i < 2; ++i) {
+      s.patch[i] = (int8_t)h[i]->patch; s.g[i] = (int8_t)h[i]->g; s.dy[i] = (int8_t)h[i]->dy;
+      s.dx[i] = (int8_t)h[i]->dx; s.tap[i] = (int8_t)h[i]->tap;
+    }
+    steps.push_back(s);
+  };
+  // halves of one (class, slot) group are emitted in increasing shared-memory offset so LBO >= 0
+  auto emit_group = [&](int slot_rel, int cls, bool& first, std::vector<Half>& taps) {
+    if (G % 2 == 0) {
+      for (const Half& t : taps)
+        for (int g = 0; g < G; g += 2) {
+          Half a = t, b2 = t;
+          a.g = g; b2.g = g + 1;
+          emit(slot_rel, cls, first, a, b2);
+          first = false;
+        }
+    } else {  // G == 1: pair consecutive taps; an odd tail is paired with zero weights on the next row
+      for (size_t i = 0; i < taps.size(); i += 2) {
+        Half a = taps[i], b2;
+        if (i + 1 < taps.size()) b2 = taps[i + 1];
+        else { b2 = a; b2.dx += 1; b2.tap = -1; }
+        emit(slot_rel, cls, first, a, b2);
+        first = false;
+      }
+    }
+  };
+  if (G != 1 && G % 2 != 0) return false;
+  if (mode == MODE_S1) {
+    bool first = true;
+    for (int kd = 0; kd < 3; ++kd) {
+      std::vector<Half> taps;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) taps.push_back({0, 0, kh, kw, kd * 9 + kh * 3 + kw});
+      emit_group(kd, 0, first, taps);
+    }
+  } else if (mode == MODE_S2) {
+    bool first = true;
+    for (int kd = 0; kd < 3; ++kd) {
+      std::vector<Half> taps;  // even-row patch first (lower addresses), then the odd-row patch
+      for (int kw = 0; kw < 3; ++kw) taps.push_back({0, 0, 0, kw, kd * 9 + 1 * 3 + kw});
+      for (int kw = 0; kw < 3; ++kw) taps.push_back({1, 0, 0, kw, kd * 9 + 0 * 3 + kw});
+      for (int kw = 0; kw < 3; ++kw) taps.push_back({1, 0, 1, kw, kd * 9 + 2 * 3 + kw});
+      emit_group(kd, 0, first, taps);
+    }
+  } else {
+    if (G % 2) return false;
+    // output o = 2*i - 1 + t: parity 0 <- (t=1, i=j); parity 1 <- (t=2, i=j), (t=0, i=j+1)
+    auto dim_taps = [](int p, int (&t)[2], int (&s)[2]) { if (p == 0) { t[0] = 1; s[0] = 0; return 1; } t[0] = 2; s[0] = 0; t[1] = 0; s[1] = 1; return 2; };
+    for (int pd = 0; pd < 2; ++pd)
+      for (int ph = 0; ph < 2; ++ph)
+        for (int pw = 0; pw < 2; ++pw) {
+          const int cls = pd * 4 + ph * 2 + pw;
+          bool first = true;
+          int td[2], sd[2], th[2], sh[2], tw[2], sw[2];
+          int nd = dim_taps(pd, td, sd), nh = dim_taps(ph, th, sh), nw = dim_taps(pw, tw, sw);
+          for (int a = 0; a < nd; ++a) {
+            std::vector<Half> taps;
+            for (int bq = 0; bq < nh; ++bq)
+              for (int c = 0; c < nw; ++c) taps.push_back({0, 0, sh[bq], sw[c], td[a] * 9 + th[bq] * 3 + tw[c]});
+            emit_group(sd[a], cls, first, taps);
+          }
+        }
+  }
+  return (int)steps.size() <= kMaxSteps;
+}
+
+// how many output-channel blobs a layer is split into so that weights + ring fit in shared memory
+static int n_split(int Cin, int Cout) { return (Cin >= 64 && Cout >= 64) ? 2 : 1; }
+
+static size_t blob_bytes(int nsteps, int N) { return (size_t)weights_offset(nsteps) + (size_t)nsteps * 2 * N * 16; }
+
+size_t conv3d_tc_packed_bytes(const damvs_conv3d_desc* d) {
+  std::vector<StepSrc> steps;
+  if (!build_program(mode_of(d), d->Cin / 8, steps)) return 0;
+  int split = n_split(d->Cin, d->Cout);
+  int N = padded_n(d->Cout / split);
+  return (blob_bytes((int)steps.size(), N) + 255) / 256 * 256 * split;
+}
+
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, uint8_t* __restrict__ blob, int Cin, int Cout, int co_end,
+                                      int transposed, int N, int n0, int nsteps) {
+  const StepSrc* steps = reinterpret_cast<const StepSrc*>(blob + steps_offset());
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(blob + weights_offset(nsteps));
+  int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [nsteps][2][N][8]
+  if (i >= nsteps * 2 * N * 8) return;
+  int j = i & 7, n = (i >> 3) % N, h = (i / (8 * N)) & 1, s = i / (16 * N);
+  StepSrc st = steps[s];
+  int co = n0 + n, ci = st.g[h] * 8 + j, tap = st.tap[h];
+  float v = 0.f;
+  if (tap >= 0 && co < co_end)
+    v = transposed ? w[((size_t)ci * Cout + co) * 27 + tap] : w[((size_t)co * Cin + ci) * 27 + tap];
+  dst[i] = __float2bfloat16_rn(v);
+}
+
+int conv3d_tc_pack(const damvs_conv3d_desc* d, const float* weight, void* packed, cudaStream_t st) {
+  std::vector<StepSrc> steps;
+  const int mode = mode_of(d), G = d->Cin / 8;
+  if (!build_program(mode, G, steps)) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cin=%d not supported", d->Cin);
+  if (d->Cout > 64 && !d->plain_out) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cout=%d > 64", d->Cout);
+  const int split = n_split(d->Cin, d->Cout);
+  const int cper = d->Cout / split;
+  const int N = padded_n(cper);
+  const int nsteps = (int)steps.size();
+  const size_t bb = (blob_bytes(nsteps, N) + 255) / 256 * 256;
+  for (int k = 0; k < split; ++k) {
+    uint8_t* blob = (uint8_t*)packed + k * bb;
+    PackedHeader h{};
+    h.magic = kMagic; h.mode = mode; h.Cin = d->Cin; h.Cout = d->Cout; h.N = N; h.nsteps = nsteps;
+    h.ncls = mode == MODE_T ? 8 : 1; h.n0 = k * cper; h.blob_bytes = (int)bb; h.nblobs = split;
+    DAMVS_CUDA_OK(cudaMemcpyAsync(blob, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    DAMVS_CUDA_OK(cudaMemcpyAsync(blob + steps_offset(), steps.data(), nsteps * sizeof(StepSrc), cudaMemcpyHostToDevice, st));
+    int total = nsteps * 2 * N * 8;
+    // the blob computes channels [n0, n0 + cper); rows beyond that are zero padding
+    pack_weight_tc_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, blob, d->Cin, d->Cout, (k + 1) * cper, d->transposed, N,
+                                                              k * cper, nsteps);
+    DAMVS_LAUNCH_OK("pack_weight_tc kernel");
+  }
+  // the host staging buffers above are read by the async copies: make them safe to drop
+  DAMVS_CUDA_OK(cudaStreamSynchronize(st));
+  return DAMVS_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  });
+  return fn;
+}
+
+// G8 bf16 volume [BG][D][H][W*8] viewed with rows (row0, row0 + row_step, ...)
+static int make_map(CUtensorMap* m, const void* base, int BG, int D, int H, int W, int row0, int row_step, int box_rows, int G) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(DAMVS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
+  const int nrows = (H - row0 + row_step - 1) / row_step;
+  cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)(nrows > 0 ? nrows : 1), (cuuint64_t)D, (cuuint64_t)BG};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 16 * row_step, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+  cuuint32_t box[4] = {(cuuint32_t)kP * 8, (cuuint32_t)box_rows, 1, (cuuint32_t)G};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  void* addr = (void*)((const uint8_t*)base + (size_t)row0 * W * 16);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(DAMVS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) W=%d H=%d D=%d BG=%d rows=%d", (int)r, W, H, D, BG, box_rows);
+  return DAMVS_OK;
+}
+
+template <int MODE, int N, int MC>
+static int launch_one(const damvs_conv3d_desc* d, const TcParams& P, const void* in, cudaStream_t st) {
+  using G_ = Geo<MODE>;
+  const int G = d->Cin / 8;
+  CUtensorMap m0, m1;
+  int rc;
+  if (MODE == MODE_S2) {
+    if ((rc = make_map(&m0, in, d->B * G, d->Din, d->Hin, d->Win, 0, 2, G_::rows0(MC), G))) return rc;
+    if ((rc = make_map(&m1, in, d->B * G, d->Din, d->Hin, d->Win, 1, 2, G_::rows1(MC), G))) return rc;
+  } else {
+    if ((rc = make_map(&m0, in, d->B * G, d->Din, d->Hin, d->Win, 0, 1, G_::rows0(MC), G))) return rc;
+    m1 = m0;
+  }
+  // nsteps comes from the program (recomputed on the host; cheap)
+  std::vector<StepSrc> steps;
+  build_program(MODE, G, steps);
+  const int nsteps = (int)steps.size();
+  const int slot_stride = G * (G_::rows0(MC) + G_::rows1(MC)) * kP * 16 + 128;
+  size_t smem = (size_t)kSlots * slot_stride + (size_t)nsteps * 2 * N * 16 + kMaxSteps * sizeof(StepRt) + 2 * N * sizeof(float) +
+                (2 * kSlots + 4) * sizeof(uint64_t) + 16;
+  if (smem > 227 * 1024) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: needs %zu bytes of shared memory", smem);
+  auto kern = conv3d_tc_kernel<MODE, N, MC>;
+  DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int TH = 4 * MC;
+  const int tiles_h = MODE == MODE_T ? d->Hin : P.Hout, tiles_w = MODE == MODE_T ? d->Win : P.Wout;
+  dim3 grid((tiles_w + G_::TW - 1) / G_::TW, (tiles_h + TH - 1) / TH, d->B);
+  kern<<<grid, 192, smem, st>>>(m0, m1, P);
+  DAMVS_LAUNCH_OK("conv3d_tc kernel");
+  return DAMVS_OK;
+}
+
+int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* packed, const float* scale, const float* shift,
+                     const void* skip, void* out, cudaStream_t st) {
+  if (d->in_dtype != DAMVS_BF16 || (!d->plain_out && d->out_dtype != DAMVS_BF16))
+    return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: bf16 volumes only");
+  if (d->plain_out && (d->transposed || d->stride != 1)) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: plain_out is stride-1 only");
+  const int mode = mode_of(d), G = d->Cin / 8;
+  if (G != 1 && G % 2) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cin=%d not supported", d->Cin);
+  if (d->Cout > 64) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cout=%d > 64", d->Cout);
+  if (mode == MODE_S2 && ((d->Hin & 1) || (d->Win & 1) || (d->Din & 1)))
+    return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: stride-2 needs even input extents");
+  const int split = n_split(d->Cin, d->Cout);
+  const int cper = d->Cout / split;
+  const int N = padded_n(cper);
+  TcParams P{};
+  P.scale = scale; P.shift = shift; P.skip = (const __nv_bfloat16*)skip; P.out = out;
+  P.B = d->B; P.G = G; P.Din = d->Din; P.Hin = d->Hin; P.Win = d->Win;
+  if (d->transposed) { P.Dout = 2 * d->Din; P.Hout = 2 * d->Hin; P.Wout = 2 * d->Win; P.niter = d->Din; }
+  else { P.Dout = (d->Din - 1) / d->stride + 1; P.Hout = (d->Hin - 1) / d->stride + 1; P.Wout = (d->Win - 1) / d->stride + 1; P.niter = P.Dout; }
+  P.out_G = d->plain_out ? 1 : d->Cout / 8; P.relu = d->relu; P.plain_out = d->plain_out;
+  std::vector<StepSrc> steps;
+  if (!build_program(mode, G, steps)) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: no program for Cin=%d", d->Cin);
+  const size_t bb = (blob_bytes((int)steps.size(), N) + 255) / 256 * 256;
+  for (int k = 0; k < split; ++k) {
+    P.blob = (const uint8_t*)packed + k * bb;
+    P.n0 = k * cper; P.out_g0 = (k * cper) / 8; P.Cout = d->plain_out ? 1 : (k + 1) * cper;
+    int rc;
+#define GO(MODE_, N_, MC_) rc = launch_one<MODE_, N_, MC_>(d, P, in, st)
+    if (mode == MODE_S1) {
+      if (N == 16) GO(MODE_S1, 16, 4); else if (N == 32) GO(MODE_S1, 32, 2); else GO(MODE_S1, 64, 1);
+    } else if (mode == MODE_S2) {
+      if (N == 16) GO(MODE_S2, 16, 2); else if (N == 32) GO(MODE_S2, 32, 2); else GO(MODE_S2, 64, 1);
+    } else {
+      if (N == 16) GO(MODE_T, 16, 2); else if (N == 32) GO(MODE_T, 32, 1); else return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: transposed Cout=%d", d->Cout);
+    }
+#undef GO
+    if (rc) return rc;
+  }
+  return DAMVS_OK;
 }
 
 }  // namespace damvs

@@ -60,8 +60,14 @@ def conv_impl_for(cin: int, cout: int, stride: int, transposed: bool) -> int:
 
 
 def tc_supported(cin: int, cout: int, stride: int, transposed: bool) -> bool:
-    """Layer shapes conv3d_tc.cu covers (bf16 in/out)."""
-    return False
+    """Layer shapes conv3d_tc.cu covers (bf16 in/out): Cin = 8 or a multiple of 16, Cout <= 64
+    (<= 32 for the transposed conv, whose 8 parity classes share the 512 TMEM columns)."""
+    g = cin // 8
+    if cin % 8 or not (g == 1 or g % 2 == 0) or g > 8:
+        return False
+    if transposed:
+        return g % 2 == 0 and cout <= 32
+    return cout <= 64
 
 
 # --------------------------------------------------------------------------

@@ -1,0 +1,107 @@
+"""tcgen05 implicit-GEMM conv blocks against torch fp32 convolutions on bf16-representable data.
+
+Inputs and weights are rounded to bf16 first, so the only differences left are the fp32
+accumulation order and the final bf16 rounding of the output (relative 2^-8)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def _bf(t):
+    return t.bfloat16().float()
+
+
+CASES = [
+    # cin, cout, stride, transposed, (D, H, W)
+    (8, 8, 1, False, (8, 16, 24)),
+    (8, 8, 1, False, (5, 19, 67)),      # ragged: several tiles, partial last tile
+    (16, 8, 1, False, (4, 9, 33)),
+    (32, 8, 1, False, (6, 18, 40)),
+    (16, 16, 1, False, (4, 12, 36)),
+    (32, 32, 1, False, (3, 10, 31)),
+    (64, 64, 1, False, (2, 9, 20)),     # split into two N=32 launches
+    (8, 16, 2, False, (8, 16, 24)),
+    (8, 16, 2, False, (6, 22, 70)),
+    (16, 32, 2, False, (4, 12, 36)),
+    (32, 64, 2, False, (4, 8, 34)),
+    (64, 32, 1, True, (2, 5, 9)),
+    (32, 16, 1, True, (3, 9, 33)),
+    (16, 8, 1, True, (4, 11, 40)),
+]
+
+
+@pytest.mark.parametrize("cin,cout,stride,transposed,ext", CASES)
+def test_tc_conv_block_matches_torch(cin, cout, stride, transposed, ext):
+    import damvsnet_b200 as dm
+    g = torch.Generator().manual_seed(cin * 1000 + cout * 10 + stride + (5 if transposed else 0))
+    if transposed:
+        blk = dm.Deconv3d(cin, cout, stride=2, padding=1, output_padding=1)
+    else:
+        blk = dm.Conv3d(cin, cout, stride=stride, padding=1)
+    with torch.no_grad():
+        blk.conv.weight.copy_(_bf(blk.conv.weight))
+        blk.bn.weight.copy_(0.8 + 0.4 * torch.rand(cout, generator=g))
+        blk.bn.bias.copy_(0.1 * torch.randn(cout, generator=g))
+        blk.bn.running_mean.copy_(0.05 * torch.randn(cout, generator=g))
+        blk.bn.running_var.copy_(0.5 + torch.rand(cout, generator=g))
+    blk = blk.eval()
+    B = 2
+    x = _bf(torch.randn(B, cin, *ext, generator=g))
+    with torch.no_grad():
+        want = torch.relu(blk.bn(blk.conv(x)))
+    skip = _bf(torch.randn(want.shape, generator=g))
+    blk = blk.to(dev())
+    with dm.precision("bf16", "tcgen05"):
+        vol = dm.G8Volume.from_ncdhw(x.to(dev()), torch.bfloat16)
+        got = blk.forward_g8(vol).to_ncdhw().cpu()
+        sk = dm.G8Volume.from_ncdhw(skip.to(dev()), torch.bfloat16)
+        got_skip = blk.forward_g8(vol, skip=sk).to_ncdhw().cpu()
+    torch.cuda.synchronize()
+    assert got.shape == want.shape
+    tol = 2 ** -7
+    err = (got - want).abs()
+    assert (err <= tol * want.abs() + 2e-3).all(), (err.max().item(), (err / want.abs().clamp_min(1e-2)).max().item())
+    ws = want + skip
+    err = (got_skip - ws).abs()
+    assert (err <= tol * ws.abs() + tol * want.abs() + 4e-3).all(), err.max().item()
+
+
+def test_tc_prob_conv_plain_output():
+    import damvsnet_b200 as dm
+    from damvsnet_b200 import ops
+    g = torch.Generator().manual_seed(9)
+    w = _bf(torch.randn(1, 8, 3, 3, 3, generator=g) * 0.2)
+    x = _bf(torch.randn(2, 8, 8, 13, 45, generator=g))
+    want = F.conv3d(x, w, None, padding=1).squeeze(1)
+    packed = ops.conv3d_pack_weight(w.to(dev()), 8, 1, False, ops.CONV_TCGEN05)
+    vol = dm.G8Volume.from_ncdhw(x.to(dev()), torch.bfloat16)
+    got = ops.conv3d(vol, packed, None, None, 1, 1, False, False, None, torch.float32, True, ops.CONV_TCGEN05).cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max() < 1e-4 * max(1.0, want.abs().max().item())
+
+
+@pytest.mark.parametrize("stage", [0, 1, 2])
+def test_cost_reg_net_tc_vs_direct_bf16(stage):
+    """Whole U-Net: tcgen05 path against the direct fp32-accumulate kernels on the same bf16 storage."""
+    import damvsnet_b200 as dm
+    from damvsnet_b200 import synthetic
+    sd = synthetic.hot_path_state_dict(seed=2)
+    cin = synthetic.STAGE_CHANNELS[stage]
+    cr = dm.CostRegNet(cin, 8).eval()
+    pre = f"cost_regularization.{stage}."
+    cr.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, strict=True)
+    cr = cr.to(dev())
+    x = (torch.rand(1, cin, 8, 24, 40) * 0.5).to(dev())
+    with dm.precision("bf16", "direct"):
+        a = cr(x).cpu()
+    with dm.precision("bf16", "tcgen05"):
+        b = cr(x).cpu()
+    scale = a.abs().max().item()
+    assert (a - b).abs().max().item() < 3e-2 * max(scale, 1.0), ((a - b).abs().max().item(), scale)
+    assert (a - b).abs().mean().item() < 3e-3 * max(scale, 1.0)
