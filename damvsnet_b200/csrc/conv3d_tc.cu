@@ -490,8 +490,15 @@ static int make_map(CUtensorMap* m, const void* base, int BG, int D, int H, int 
   return DAMVS_OK;
 }
 
+static size_t smem_need(int mode, int G, int N, int MC, int nsteps) {
+  const int rows = mode == MODE_S1 ? 4 * MC + 2 : (mode == MODE_T ? 4 * MC + 1 : 8 * MC + 1);
+  const size_t slot_stride = (size_t)G * rows * kP * 16 + 128;
+  return kSlots * slot_stride + (size_t)nsteps * 2 * N * 16 + kMaxSteps * sizeof(StepRt) + 2 * N * sizeof(float) +
+         (2 * kSlots + 4) * sizeof(uint64_t) + 16;
+}
+
 template <int MODE, int N, int MC>
-static int launch_one(const damvs_conv3d_desc* d, const TcParams& P, const void* in, cudaStream_t st) {
+static int launch_one(const damvs_conv3d_desc* d, const TcParams& P, const void* in, int nsteps, cudaStream_t st) {
   using G_ = Geo<MODE>;
   const int G = d->Cin / 8;
   CUtensorMap m0, m1;
@@ -503,14 +510,7 @@ static int launch_one(const damvs_conv3d_desc* d, const TcParams& P, const void*
     if ((rc = make_map(&m0, in, d->B * G, d->Din, d->Hin, d->Win, 0, 1, G_::rows0(MC), G))) return rc;
     m1 = m0;
   }
-  // nsteps comes from the program (recomputed on the host; cheap)
-  std::vector<StepSrc> steps;
-  build_program(MODE, G, steps);
-  const int nsteps = (int)steps.size();
-  const int slot_stride = G * (G_::rows0(MC) + G_::rows1(MC)) * kP * 16 + 128;
-  size_t smem = (size_t)kSlots * slot_stride + (size_t)nsteps * 2 * N * 16 + kMaxSteps * sizeof(StepRt) + 2 * N * sizeof(float) +
-                (2 * kSlots + 4) * sizeof(uint64_t) + 16;
-  if (smem > 227 * 1024) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: needs %zu bytes of shared memory", smem);
+  const size_t smem = smem_need(MODE, G, N, MC, nsteps);
   auto kern = conv3d_tc_kernel<MODE, N, MC>;
   DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int TH = 4 * MC;
@@ -519,6 +519,17 @@ static int launch_one(const damvs_conv3d_desc* d, const TcParams& P, const void*
   kern<<<grid, 192, smem, st>>>(m0, m1, P);
   DAMVS_LAUNCH_OK("conv3d_tc kernel");
   return DAMVS_OK;
+}
+
+// largest M-chunk count (tile height 4*MC rows) whose ring + weights fit in shared memory and TMEM
+static int pick_mc(int mode, int G, int N, int nsteps, int tile_rows_avail) {
+  const int cap = mode == MODE_T ? 32 / N : (N == 64 ? 2 : 4);  // T: 8 classes * MC * N * 2 buffers <= 512 columns
+  for (int mc = 4; mc >= 1; mc >>= 1) {
+    if (mc > cap) continue;
+    if (mc > 1 && 4 * (mc / 2) >= tile_rows_avail) continue;      // do not pad a short volume with empty tile rows
+    if (smem_need(mode, G, N, mc, nsteps) <= 227 * 1024) return mc;
+  }
+  return 0;
 }
 
 int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* packed, const float* scale, const float* shift,
@@ -546,15 +557,19 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
   for (int k = 0; k < split; ++k) {
     P.blob = (const uint8_t*)packed + k * bb;
     P.n0 = k * cper; P.out_g0 = (k * cper) / 8; P.Cout = d->plain_out ? 1 : (k + 1) * cper;
-    int rc;
-#define GO(MODE_, N_, MC_) rc = launch_one<MODE_, N_, MC_>(d, P, in, st)
-    if (mode == MODE_S1) {
-      if (N == 16) GO(MODE_S1, 16, 4); else if (N == 32) GO(MODE_S1, 32, 2); else GO(MODE_S1, 64, 1);
-    } else if (mode == MODE_S2) {
-      if (N == 16) GO(MODE_S2, 16, 2); else if (N == 32) GO(MODE_S2, 32, 2); else GO(MODE_S2, 64, 1);
-    } else {
-      if (N == 16) GO(MODE_T, 16, 2); else if (N == 32) GO(MODE_T, 32, 1); else return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: transposed Cout=%d", d->Cout);
-    }
+    int rc = -1;
+    const int nsteps = (int)steps.size();
+    const int mc = pick_mc(mode, G, N, nsteps, mode == MODE_T ? d->Hin : P.Hout);
+    if (mc == 0) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cin=%d Cout=%d does not fit in shared memory", d->Cin, d->Cout);
+#define GO(MODE_, N_, MC_) if (mode == MODE_ && N == N_ && mc == MC_) rc = launch_one<MODE_, N_, MC_>(d, P, in, nsteps, st)
+    GO(MODE_S1, 16, 4); GO(MODE_S1, 16, 2); GO(MODE_S1, 16, 1);
+    GO(MODE_S1, 32, 4); GO(MODE_S1, 32, 2); GO(MODE_S1, 32, 1);
+    GO(MODE_S1, 64, 2); GO(MODE_S1, 64, 1);
+    GO(MODE_S2, 16, 4); GO(MODE_S2, 16, 2); GO(MODE_S2, 16, 1);
+    GO(MODE_S2, 32, 4); GO(MODE_S2, 32, 2); GO(MODE_S2, 32, 1);
+    GO(MODE_S2, 64, 2); GO(MODE_S2, 64, 1);
+    GO(MODE_T, 16, 2); GO(MODE_T, 16, 1); GO(MODE_T, 32, 1);
+    if (rc == -1) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: no kernel for mode=%d N=%d MC=%d", mode, N, mc);
 #undef GO
     if (rc) return rc;
   }
