@@ -101,6 +101,11 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
   const int slot_stride = patch0_bytes + patch1_bytes + 128;
   const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(P.blob);
   const int nsteps = hdr->nsteps;
+  if (hdr->magic != kMagic || hdr->mode != MODE || hdr->N != N) {
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+      printf("damvs: packed conv weights were built for another layer type (mode %d N %d, kernel mode %d N %d)\n", hdr->mode, hdr->N, MODE, N);
+    __trap();
+  }
   uint8_t* sA = smem;
   uint8_t* sB = sA + kSlots * slot_stride;
   StepRt* sProg = reinterpret_cast<StepRt*>(sB + nsteps * 2 * N * 16);

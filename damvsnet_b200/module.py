@@ -59,7 +59,7 @@ class _ConvBlock(nn.Module):
         if hit is not None and hit[0] == ver:
             return hit[1]
         cin, cout = self.in_channels, self.out_channels
-        packed = ops.conv3d_pack_weight(w.detach().float(), cin, cout, self.transposed, impl)
+        packed = ops.conv3d_pack_weight(w.detach().float(), cin, cout, self.transposed, impl, self.stride)
         if bn is not None:
             scale, shift = _bn_affine(bn)
         elif self.conv.bias is not None:

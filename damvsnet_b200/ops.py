@@ -237,10 +237,11 @@ def conv_desc(b, cin, cout, din, hin, win, stride, transposed, relu, in_dtype, o
                     impl=impl)
 
 
-def conv3d_pack_weight(weight: torch.Tensor, cin: int, cout: int, transposed: bool, impl: int) -> torch.Tensor:
-    """PyTorch-layout fp32 conv weight -> the packed buffer `impl` consumes (uint8 tensor)."""
+def conv3d_pack_weight(weight: torch.Tensor, cin: int, cout: int, transposed: bool, impl: int, stride: int = 1) -> torch.Tensor:
+    """PyTorch-layout fp32 conv weight -> the packed buffer `impl` consumes (uint8 tensor).
+    The tcgen05 buffer embeds the layer's MMA program, which depends on stride / transposed."""
     _need(weight, "weight", torch.float32, 5)
-    desc = conv_desc(1, cin, cout, 1, 1, 1, 1, transposed, 0, torch.float32, torch.float32, cout == 1, impl)
+    desc = conv_desc(1, cin, cout, 1, 1, 1, stride, transposed, 0, torch.float32, torch.float32, cout == 1, impl)
     lib = _lib.load()
     nbytes = lib.damvs_conv3d_packed_weight_bytes(ctypes.byref(desc))
     if nbytes == 0:

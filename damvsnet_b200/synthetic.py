@@ -140,7 +140,7 @@ def hot_path_state_dict(in_channels=STAGE_CHANNELS, base_channels=(8, 8, 8), see
         shape = (cin, cout, k, k, k) if transposed else (cout, cin, k, k, k)
         return (torch.rand(shape, generator=g) * 2 - 1) * bound * math.sqrt(3.0)
 
-    def bn(prefix, c, mean_scale=0.05, var_lo=0.02, var_hi=0.08):
+    def bn(prefix, c, mean_scale=0.05, var_lo=0.15, var_hi=0.45):
         sd[prefix + ".weight"] = 0.8 + 0.4 * torch.rand(c, generator=g)
         sd[prefix + ".bias"] = 0.1 * torch.randn(c, generator=g)
         sd[prefix + ".running_mean"] = mean_scale * torch.randn(c, generator=g)
