@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--ndepths", default="48,32,8")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="print a per-layer device-time table to stderr")
     return ap.parse_args()
 
 
@@ -263,6 +264,11 @@ def run_ours(args):
             for _ in range(3):
                 runner.run_device(dev_stages)
         summ = timer.summary()
+        if args.detail:
+            for tag, d in timer.summary(detail=True).items():
+                ms = d["ms"] / d["calls"]
+                print(f"  {tag:48s} {ms * 1e3:9.1f} us  {d['bytes'] / d['calls'] / ms / 1e6:8.0f} GB/s  {d['flops'] / d['calls'] / ms / 1e9:8.1f} TF/s",
+                      file=sys.stderr)
         kernels = {}
         for tag, d in summ.items():
             per_step_ms = d["ms"] / 3

@@ -53,10 +53,10 @@ struct PackedHeader {  // 64 bytes
   int32_t mode, Cin, Cout, N, nsteps, ncls, n0;  // n0: first output channel this blob computes
   int32_t blob_bytes, nblobs, pad[6];
 };
+// Launch-time form of a step, passed in the kernel parameter (constant) space so the MMA issuer reads it
+// with uniform loads: x = (A offset from the slot base)>>4 | (LBO>>4)<<16, y = slot_rel | cls<<2 | first<<7.
 struct StepRt {
-  uint32_t a_off;  // bytes from the slot base
-  uint16_t lbo;    // bytes
-  uint8_t slot_rel, cls_first;  // bit 7: first
+  uint32_t a_word, info;
 };
 
 struct TcParams {
@@ -67,7 +67,8 @@ struct TcParams {
   void* out;
   int B, G, Din, Hin, Win, Dout, Hout, Wout;
   int out_G, out_g0;  // output volume's group count and first group written by this launch
-  int n0, Cout, relu, plain_out, niter;
+  int n0, Cout, relu, plain_out, niter, nsteps;
+  StepRt prog[kMaxSteps];
 };
 
 __host__ __device__ inline int steps_offset() { return (int)sizeof(PackedHeader); }
@@ -100,16 +101,15 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
   const int patch1_bytes = G * G_::rows1(MC) * kP * 16;
   const int slot_stride = patch0_bytes + patch1_bytes + 128;
   const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(P.blob);
-  const int nsteps = hdr->nsteps;
-  if (hdr->magic != kMagic || hdr->mode != MODE || hdr->N != N) {
+  const int nsteps = P.nsteps;
+  if (hdr->magic != kMagic || hdr->mode != MODE || hdr->N != N || hdr->nsteps != nsteps) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
       printf("damvs: packed conv weights were built for another layer type (mode %d N %d, kernel mode %d N %d)\n", hdr->mode, hdr->N, MODE, N);
     __trap();
   }
   uint8_t* sA = smem;
   uint8_t* sB = sA + kSlots * slot_stride;
-  StepRt* sProg = reinterpret_cast<StepRt*>(sB + nsteps * 2 * N * 16);
-  float* sScale = reinterpret_cast<float*>(sProg + kMaxSteps);
+  float* sScale = reinterpret_cast<float*>(sB + nsteps * 2 * N * 16);
   float* sShift = sScale + N;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + N);
   uint64_t* full = bars;
@@ -128,22 +128,6 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
     const uint4* wsrc = reinterpret_cast<const uint4*>(P.blob + weights_offset(nsteps));
     uint4* wdst = reinterpret_cast<uint4*>(sB);
     for (int i = threadIdx.x; i < nsteps * 2 * N; i += blockDim.x) wdst[i] = __ldg(wsrc + i);
-    const StepSrc* src = reinterpret_cast<const StepSrc*>(P.blob + steps_offset());
-    for (int s = threadIdx.x; s < nsteps; s += blockDim.x) {
-      StepSrc st = src[s];
-      uint32_t off[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        int rows = st.patch[h] ? G_::rows1(MC) : G_::rows0(MC);
-        off[h] = (st.patch[h] ? patch0_bytes : 0) + ((st.g[h] * rows + st.dy[h]) * kP + st.dx[h]) * 16;
-      }
-      StepRt rt;
-      rt.a_off = off[0];
-      rt.lbo = (uint16_t)(off[1] - off[0]);
-      rt.slot_rel = (uint8_t)st.slot_rel;
-      rt.cls_first = (uint8_t)(st.cls | (st.first ? 0x80 : 0));
-      sProg[s] = rt;
-    }
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
       int co = P.n0 + i;
       bool ok = co < P.Cout;
@@ -192,36 +176,44 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-      int next_wait = 0;
-      for (int it = 0; it < niter; ++it) {
-        const int need = it * G_::adv + G_::span - 1;
-        while (next_wait <= need) {
-          mbar_wait(&full[next_wait % kSlots], (next_wait / kSlots) & 1);
-          ++next_wait;
-        }
-        const int buf = it & 1;
-        if (it >= 2) mbar_wait(&tmem_empty[buf], ((it >> 1) - 1) & 1);
-        tc_fence_after();
-        const uint32_t dbase = tmem_base + buf * ACC_COLS;
-        for (int s = 0; s < nsteps; ++s) {
-          const StepRt st = sProg[s];
-          const int slot = (it * G_::adv + st.slot_rel) % kSlots;
-          const uint32_t a_addr = a_base + slot * slot_stride + st.a_off;
-          const uint64_t bdesc = smem_desc(b_base + s * (2 * N * 16), N * 16, 128);
-          const uint32_t cls = st.cls_first & 0x7f, acc = (st.cls_first & 0x80) ? 0u : 1u;
+    // ===== MMA issuer: the whole warp walks the (uniform) program, one elected lane issues =====
+    const bool leader = elect_one();
+    const uint32_t a_base16 = smem_u32(sA) >> 4, b_base16 = smem_u32(sB) >> 4;
+    const uint32_t slot16 = (uint32_t)slot_stride >> 4;
+    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+    int next_wait = 0;
+    for (int it = 0; it < niter; ++it) {
+      const int need = it * G_::adv + G_::span - 1;
+      while (next_wait <= need) {
+        mbar_wait(&full[next_wait % kSlots], (next_wait / kSlots) & 1);
+        ++next_wait;
+      }
+      const int buf = it & 1;
+      if (it >= 2) mbar_wait(&tmem_empty[buf], ((it >> 1) - 1) & 1);
+      tc_fence_after();
+      const uint32_t dbase = tmem_base + buf * ACC_COLS;
+      const uint32_t so0 = a_base16 + ((it * G_::adv + 0) % kSlots) * slot16;
+      const uint32_t so1 = a_base16 + ((it * G_::adv + 1) % kSlots) * slot16;
+      const uint32_t so2 = a_base16 + ((it * G_::adv + 2) % kSlots) * slot16;
+#pragma unroll 1
+      for (int s = 0; s < nsteps; ++s) {
+        const StepRt st = P.prog[s];
+        const uint32_t rel = st.info & 3u, cls = (st.info >> 2) & 15u, acc = (st.info >> 7) & 1u ? 0u : 1u;
+        const uint32_t a_lo = st.a_word + (rel == 0 ? so0 : (rel == 1 ? so1 : so2));
+        const uint32_t b_lo = (b_base16 + s * (2 * N)) | ((uint32_t)N << 16);  // LBO = N*16 bytes
+        const uint64_t bdesc = ((uint64_t)DESC_HI << 32) | b_lo;
 #pragma unroll
-          for (int c = 0; c < MC; ++c) {
-            const uint64_t adesc = smem_desc(a_addr + c * 128 * 16, st.lbo, 128);
-            mma_bf16_ss(dbase + (cls * MC + c) * N, adesc, bdesc, IDESC, acc);
-          }
+        for (int c = 0; c < MC; ++c) {
+          const uint64_t adesc = ((uint64_t)DESC_HI << 32) | (a_lo + c * 128);
+          if (leader) mma_bf16_ss(dbase + (cls * MC + c) * N, adesc, bdesc, IDESC, acc);
         }
+      }
+      if (leader) {
         mma_commit(&tmem_full[buf]);
 #pragma unroll
         for (int a = 0; a < G_::adv; ++a) mma_commit(&empty[(it * G_::adv + a) % kSlots]);
       }
+      __syncwarp();
     }
   } else {
     // ===== epilogue: 4 warps, warp q owns TMEM lanes 32q..32q+31 =====
@@ -498,14 +490,31 @@ static int make_map(CUtensorMap* m, const void* base, int BG, int D, int H, int 
 static size_t smem_need(int mode, int G, int N, int MC, int nsteps) {
   const int rows = mode == MODE_S1 ? 4 * MC + 2 : (mode == MODE_T ? 4 * MC + 1 : 8 * MC + 1);
   const size_t slot_stride = (size_t)G * rows * kP * 16 + 128;
-  return kSlots * slot_stride + (size_t)nsteps * 2 * N * 16 + kMaxSteps * sizeof(StepRt) + 2 * N * sizeof(float) +
+  return kSlots * slot_stride + (size_t)nsteps * 2 * N * 16 + 2 * N * sizeof(float) +
          (2 * kSlots + 4) * sizeof(uint64_t) + 16;
 }
 
 template <int MODE, int N, int MC>
-static int launch_one(const damvs_conv3d_desc* d, const TcParams& P, const void* in, int nsteps, cudaStream_t st) {
+static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, const std::vector<StepSrc>& steps, cudaStream_t st) {
   using G_ = Geo<MODE>;
   const int G = d->Cin / 8;
+  const int nsteps = (int)steps.size();
+  {
+    const int patch0_bytes = G * G_::rows0(MC) * kP * 16;
+    P.nsteps = nsteps;
+    for (int s = 0; s < nsteps; ++s) {
+      const StepSrc& src = steps[s];
+      uint32_t off[2];
+      for (int h = 0; h < 2; ++h) {
+        const int rows = src.patch[h] ? G_::rows1(MC) : G_::rows0(MC);
+        off[h] = (src.patch[h] ? patch0_bytes : 0) + ((src.g[h] * rows + src.dy[h]) * kP + src.dx[h]) * 16;
+      }
+      if (off[1] < off[0] || ((off[1] - off[0]) >> 4) >= (1u << 14) || (off[0] >> 4) >= (1u << 14))
+        return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: step %d has an unencodable operand offset", s);
+      P.prog[s].a_word = (off[0] >> 4) | (((off[1] - off[0]) >> 4) << 16);
+      P.prog[s].info = (uint32_t)src.slot_rel | ((uint32_t)src.cls << 2) | (src.first ? 0x80u : 0u);
+    }
+  }
   CUtensorMap m0, m1;
   int rc;
   if (MODE == MODE_S2) {
@@ -566,7 +575,7 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
     const int nsteps = (int)steps.size();
     const int mc = pick_mc(mode, G, N, nsteps, mode == MODE_T ? d->Hin : P.Hout);
     if (mc == 0) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cin=%d Cout=%d does not fit in shared memory", d->Cin, d->Cout);
-#define GO(MODE_, N_, MC_) if (mode == MODE_ && N == N_ && mc == MC_) rc = launch_one<MODE_, N_, MC_>(d, P, in, nsteps, st)
+#define GO(MODE_, N_, MC_) if (mode == MODE_ && N == N_ && mc == MC_) rc = launch_one<MODE_, N_, MC_>(d, P, in, steps, st)
     GO(MODE_S1, 16, 4); GO(MODE_S1, 16, 2); GO(MODE_S1, 16, 1);
     GO(MODE_S1, 32, 4); GO(MODE_S1, 32, 2); GO(MODE_S1, 32, 1);
     GO(MODE_S1, 64, 2); GO(MODE_S1, 64, 1);

@@ -275,7 +275,8 @@ def conv3d(vol: G8Volume, packed: torch.Tensor, scale: Optional[torch.Tensor], s
     flops = 2.0 * 27 * cin * cout * (b * d * h * w if transposed else vout)
     nbytes = vol.data.numel() * vol.data.element_size() + out_t.numel() * out_t.element_size() * (2 if skip is not None else 1)
     tag = "conv3d_tc" if impl == CONV_TCGEN05 else "conv3d_direct"
-    with torch.cuda.device_of(vol.data), _timed(tag, bytes=float(nbytes), flops=flops):
+    detail = f"{tag} {cin}->{cout} {'T' if transposed else 's%d' % stride} in {d}x{h}x{w}"
+    with torch.cuda.device_of(vol.data), _timed(tag, bytes=float(nbytes), flops=flops, detail=detail):
         _lib.check(_lib.load().damvs_conv3d_fwd(ctypes.byref(desc), _p(vol.data), _p(packed), _p(scale), _p(shift),
                                                 _p(None if skip is None else skip.data), _p(out_t), _stream()))
     return result
@@ -335,10 +336,12 @@ class CallTimer:
     def __exit__(self, *exc):
         CallTimer.active = None
 
-    def summary(self):
+    def summary(self, detail: bool = False):
         torch.cuda.synchronize()
         out = {}
         for tag, s, e, meta in self.records:
+            if detail:
+                tag = meta.get("detail", tag)
             d = out.setdefault(tag, {"ms": 0.0, "calls": 0, "bytes": 0.0, "flops": 0.0})
             d["ms"] += s.elapsed_time(e)
             d["calls"] += 1
