@@ -3,29 +3,36 @@
 // Replaces Conv3d / Deconv3d (reference models/module.py:117-202: nn.Conv3d /
 // nn.ConvTranspose3d + BatchNorm3d + ReLU) and the skip-adds of CostRegNet.forward
 // (models/module.py:532-541) with one kernel per layer:
-//     out = skip + relu((conv(in)) * scale + shift)
+//     out = skip + relu(conv(in) * scale + shift)
 //
-// GEMM view: M = output voxels, N = Cout (padded to a multiple of 16), K = 27 * Cin.
+// GEMM view.  M = voxels of a (4*MC rows x 32 columns) tile of one depth plane, K = 9 * Cin (the
+// (kd, kh) taps), N = 3 * CP: the three kw taps are folded into the N dimension (CP = Cout padded to
+// 16/32/64), i.e. the MMA computes Y_kw[m] = sum_{kd,kh,ci} in[m shifted by (kd,kh)] * W[kd,kh,kw]
+// for kw = 0..2 at once and the epilogue adds out[x] = Y_0[x] + Y_1[x+1] + Y_2[x+2] with two warp
+// shuffles (a tile row is 32 GEMM rows = one warp's TMEM lanes, of which 30 are real outputs).
+// Why: with both operands in shared memory a K=16 MMA re-reads its 128x16 A tile (4 KB, 32 cycles of
+// shared-memory bandwidth) whatever N is, so at N = Cout = 8..16 the un-folded form is bound by A
+// reads, not by the tensor pipe; folding kw cuts the A reads (and MMA count) by 3.
+//
 // The A operand is never materialised (no im2col):
 //   * activations live in the G8 layout ([B][C/8][D][H][W][8] bf16), so an 8-channel group of a
 //     (rows x 32 voxels) patch of one depth plane lands in shared memory, via ONE TMA box load with
 //     a contiguous 512-byte inner dimension, as a dense array of 16-byte rows -- exactly the
 //     no-swizzle K-major UMMA layout (8-row x 16-byte core matrices, SBO = 128 B);
-//   * GEMM row m = ty*32 + tx of a tile; a filter tap (kh, kw) is the SAME shared-memory patch
-//     shifted by kh*32 + kw rows, i.e. just a different descriptor start address; the two 8-channel
-//     K-halves of one K=16 MMA are two such addresses LBO bytes apart (the next channel group's
-//     plane, or -- for Cin = 8 -- the next tap);
+//   * GEMM row m = ty*32 + tx; a (kh) tap is the SAME shared-memory patch shifted by kh*32 rows, i.e.
+//     a different descriptor start address; the two 8-channel K-halves of one MMA are two such
+//     addresses LBO bytes apart (the next channel group's plane, or -- for Cin = 8 -- the next tap);
 //   * depth taps come from a ring of plane slots that slides along D, so every input plane is
 //     loaded once per CTA; out-of-range planes / rows / columns are TMA zero fill (= padding 1).
-// Columns tx >= tile width of every row are garbage GEMM rows that are computed and dropped.
 //
 // Three modes share the kernel: stride-1 conv, stride-2 conv (even/odd input rows as two patches;
-// odd output columns computed and dropped) and the k3/s2/p1/op1 transposed conv (8 output-parity
-// classes, each a 1/2/4/8-tap sub-convolution of the same input patch, own TMEM accumulator).
+// odd output columns computed and dropped) and the k3/s2/p1/op1 transposed conv (4 (d,h)-parity
+// classes x the w-parity pair folded into N, each class a 1/2/4-tap sub-convolution of the same
+// input patch with its own TMEM accumulator).
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
-// epilogue (TMEM -> registers -> BN affine / ReLU / skip -> 16-byte stores).  Accumulators are
-// double buffered in TMEM so the epilogue of plane z overlaps the MMAs of plane z+1.
+// epilogue (TMEM -> registers -> kw combine -> BN affine / ReLU / skip -> 16-byte stores).
+// Accumulators are double buffered in TMEM so the epilogue of plane z overlaps the MMAs of plane z+1.
 #include <mutex>
 #include <vector>
 
@@ -36,25 +43,25 @@ namespace damvs {
 
 using namespace tc;
 
-constexpr int kP = 32;       // patch pitch in voxels (one TMA box row = 32 voxels * 16 B)
-constexpr int kSlots = 4;    // depth-plane ring
-constexpr int kMaxSteps = 128;
-constexpr uint32_t kMagic = 0x44544331u;  // "DTC1"
+constexpr int kP = 32;         // patch pitch in voxels (one TMA box row = 32 voxels * 16 B)
+constexpr int kMaxSlots = 8;   // depth-plane ring (actual depth chosen per launch)
+constexpr int kMaxSteps = 96;
+constexpr uint32_t kMagic = 0x44544332u;  // "DTC2"
 
 enum { MODE_S1 = 0, MODE_S2 = 1, MODE_T = 2 };
 
 // One K=16 MMA of the per-iteration program, in layer-independent form (host-built, stored in the packed buffer).
 struct StepSrc {
   int8_t slot_rel, cls, first, pad_;
-  int8_t patch[2], g[2], dy[2], dx[2], tap[2];  // per K-half; tap < 0 => zero weights
+  int8_t patch[2], g[2], dy[2], tap[2];  // per K-half; tap = kd*3+kh (td*3+th for transposed), < 0 => zero weights
 };
 struct PackedHeader {  // 64 bytes
   uint32_t magic;
-  int32_t mode, Cin, Cout, N, nsteps, ncls, n0;  // n0: first output channel this blob computes
+  int32_t mode, Cin, Cout, CP, nsteps, ncls, n0;  // n0: first output channel this blob computes
   int32_t blob_bytes, nblobs, pad[6];
 };
 // Launch-time form of a step, passed in the kernel parameter (constant) space so the MMA issuer reads it
-// with uniform loads: x = (A offset from the slot base)>>4 | (LBO>>4)<<16, y = slot_rel | cls<<2 | first<<7.
+// with uniform loads: a_word = (A offset from the slot base)>>4 | (LBO>>4)<<16, info = slot_rel | cls<<2 | first<<7.
 struct StepRt {
   uint32_t a_word, info;
 };
@@ -67,7 +74,7 @@ struct TcParams {
   void* out;
   int B, G, Din, Hin, Win, Dout, Hout, Wout;
   int out_G, out_g0;  // output volume's group count and first group written by this launch
-  int n0, Cout, relu, plain_out, niter, nsteps;
+  int n0, Cout, relu, plain_out, niter, nsteps, nslots;
   StepRt prog[kMaxSteps];
 };
 
@@ -79,44 +86,51 @@ struct Geo {
   static constexpr int span = MODE == MODE_T ? 2 : 3;
   static constexpr int adv = MODE == MODE_S2 ? 2 : 1;
   static constexpr int p0 = MODE == MODE_T ? 0 : -1;
-  static constexpr int ncls = MODE == MODE_T ? 8 : 1;
+  static constexpr int ncls = MODE == MODE_T ? 4 : 1;
   static constexpr int TW = MODE == MODE_S1 ? 30 : (MODE == MODE_T ? 31 : 15);
   __host__ __device__ static constexpr int rows0(int MC) { return MODE == MODE_S1 ? 4 * MC + 2 : (MODE == MODE_T ? 4 * MC + 1 : 4 * MC); }
   __host__ __device__ static constexpr int rows1(int MC) { return MODE == MODE_S2 ? 4 * MC + 1 : 0; }
 };
 
-template <int MODE, int N, int MC>
+__device__ __forceinline__ float shfl_dn(uint32_t v, int d) { return __uint_as_float(__shfl_down_sync(0xffffffffu, v, d)); }
+
+template <int MODE, int CP, int MC>
 __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0,
-                                                        const __grid_constant__ CUtensorMap map1, const TcParams P) {
+                                                        const __grid_constant__ CUtensorMap map1,
+                                                        const __grid_constant__ TcParams P) {
   using G_ = Geo<MODE>;
+  constexpr int N = 3 * CP;
   constexpr int TH = 4 * MC;
   constexpr int ACC_COLS = G_::ncls * MC * N;
-  constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
-  static_assert(2 * ACC_COLS <= 512, "TMEM budget");
+  constexpr int NBUF = 2 * ACC_COLS <= 512 ? 2 : 1;
+  constexpr int NEED = NBUF * ACC_COLS;
+  constexpr int TMEM_COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
+  static_assert(ACC_COLS <= 512, "TMEM budget");
   constexpr uint32_t IDESC = idesc_bf16_m128(N);
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const int G = P.G;
   const int patch0_bytes = G * G_::rows0(MC) * kP * 16;
   const int patch1_bytes = G * G_::rows1(MC) * kP * 16;
-  const int slot_stride = patch0_bytes + patch1_bytes + 128;
+  const int slot_stride = patch0_bytes + patch1_bytes;
+  const int nslots = P.nslots;
   const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(P.blob);
   const int nsteps = P.nsteps;
-  if (hdr->magic != kMagic || hdr->mode != MODE || hdr->N != N || hdr->nsteps != nsteps) {
+  if (hdr->magic != kMagic || hdr->mode != MODE || hdr->CP != CP || hdr->nsteps != nsteps) {
     if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
-      printf("damvs: packed conv weights were built for another layer type (mode %d N %d, kernel mode %d N %d)\n", hdr->mode, hdr->N, MODE, N);
+      printf("damvs: packed conv weights were built for another layer type (mode %d CP %d, kernel mode %d CP %d)\n", hdr->mode, hdr->CP, MODE, CP);
     __trap();
   }
   uint8_t* sA = smem;
-  uint8_t* sB = sA + kSlots * slot_stride;
+  uint8_t* sB = sA + nslots * slot_stride;
   float* sScale = reinterpret_cast<float*>(sB + nsteps * 2 * N * 16);
-  float* sShift = sScale + N;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + N);
+  float* sShift = sScale + CP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + CP);
   uint64_t* full = bars;
-  uint64_t* empty = bars + kSlots;
-  uint64_t* tmem_full = bars + 2 * kSlots;
-  uint64_t* tmem_empty = bars + 2 * kSlots + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kSlots + 4);
+  uint64_t* empty = bars + kMaxSlots;
+  uint64_t* tmem_full = bars + 2 * kMaxSlots;
+  uint64_t* tmem_empty = bars + 2 * kMaxSlots + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z;
@@ -128,18 +142,15 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
     const uint4* wsrc = reinterpret_cast<const uint4*>(P.blob + weights_offset(nsteps));
     uint4* wdst = reinterpret_cast<uint4*>(sB);
     for (int i = threadIdx.x; i < nsteps * 2 * N; i += blockDim.x) wdst[i] = __ldg(wsrc + i);
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+    for (int i = threadIdx.x; i < CP; i += blockDim.x) {
       int co = P.n0 + i;
       bool ok = co < P.Cout;
       sScale[i] = ok ? (P.scale ? __ldg(P.scale + co) : 1.f) : 0.f;
       sShift[i] = ok && P.shift ? __ldg(P.shift + co) : 0.f;
     }
-    // the 128-byte tail of every slot is read by the last (discarded) GEMM rows: keep it finite
-    for (int i = threadIdx.x; i < kSlots * 32; i += blockDim.x)
-      reinterpret_cast<uint32_t*>(sA + (i / 32) * slot_stride + patch0_bytes + patch1_bytes)[i % 32] = 0u;
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kSlots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);
     fence_barrier_init();
@@ -147,7 +158,7 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
     if (MODE == MODE_S2) tma_prefetch_desc(&map1);
   }
   if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
-  fence_proxy_async();  // generic-proxy smem writes (weights, pad) -> visible to the async proxy (UMMA)
+  fence_proxy_async();  // generic-proxy smem writes (weights) -> visible to the async proxy (UMMA)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -159,9 +170,9 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
     if (lane == 0) {
       const int nplanes = (niter - 1) * G_::adv + G_::span;
       const uint32_t bytes = (uint32_t)(patch0_bytes + patch1_bytes);
+      int slot = 0, round = 0;
       for (int k = 0; k < nplanes; ++k) {
-        const int slot = k % kSlots;
-        if (k >= kSlots) mbar_wait(&empty[slot], ((k / kSlots) - 1) & 1);
+        if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
         mbar_arrive_expect_tx(&full[slot], bytes);
         uint8_t* dst = sA + slot * slot_stride;
         const int plane = k + G_::p0;
@@ -173,6 +184,7 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
           tma_load_4d(dst, &map0, &full[slot], (2 * tx0 - 1) * 8, ty0, plane, b * G);                    // even rows 2*(ty0+r)
           tma_load_4d(dst + patch0_bytes, &map1, &full[slot], (2 * tx0 - 1) * 8, ty0 - 1, plane, b * G);  // odd rows 2*(ty0+r)-1
         }
+        if (++slot == nslots) { slot = 0; ++round; }
       }
     }
   } else if (warp == 1) {
@@ -181,20 +193,24 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
     const uint32_t a_base16 = smem_u32(sA) >> 4, b_base16 = smem_u32(sB) >> 4;
     const uint32_t slot16 = (uint32_t)slot_stride >> 4;
     constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
-    int next_wait = 0;
+    int wait_slot = 0, wait_round = 0, next_wait = 0;       // full-barrier cursor
+    int base_slot = 0;                                       // slot of the first plane of this iteration
     for (int it = 0; it < niter; ++it) {
       const int need = it * G_::adv + G_::span - 1;
       while (next_wait <= need) {
-        mbar_wait(&full[next_wait % kSlots], (next_wait / kSlots) & 1);
+        mbar_wait(&full[wait_slot], wait_round & 1);
         ++next_wait;
+        if (++wait_slot == nslots) { wait_slot = 0; ++wait_round; }
       }
-      const int buf = it & 1;
-      if (it >= 2) mbar_wait(&tmem_empty[buf], ((it >> 1) - 1) & 1);
+      const int buf = NBUF == 2 ? (it & 1) : 0;
+      if (it >= NBUF) mbar_wait(&tmem_empty[buf], (NBUF == 2 ? ((it >> 1) - 1) : (it - 1)) & 1);
       tc_fence_after();
       const uint32_t dbase = tmem_base + buf * ACC_COLS;
-      const uint32_t so0 = a_base16 + ((it * G_::adv + 0) % kSlots) * slot16;
-      const uint32_t so1 = a_base16 + ((it * G_::adv + 1) % kSlots) * slot16;
-      const uint32_t so2 = a_base16 + ((it * G_::adv + 2) % kSlots) * slot16;
+      int s1 = base_slot + 1; if (s1 >= nslots) s1 -= nslots;
+      int s2 = base_slot + 2; if (s2 >= nslots) s2 -= nslots;
+      const uint32_t so0 = a_base16 + base_slot * slot16;
+      const uint32_t so1 = a_base16 + s1 * slot16;
+      const uint32_t so2 = a_base16 + s2 * slot16;
 #pragma unroll 1
       for (int s = 0; s < nsteps; ++s) {
         const StepRt st = P.prog[s];
@@ -211,18 +227,21 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
       if (leader) {
         mma_commit(&tmem_full[buf]);
 #pragma unroll
-        for (int a = 0; a < G_::adv; ++a) mma_commit(&empty[(it * G_::adv + a) % kSlots]);
+        for (int a = 0; a < G_::adv; ++a) {
+          int rs = base_slot + a; if (rs >= nslots) rs -= nslots;
+          mma_commit(&empty[rs]);
+        }
       }
+      base_slot += G_::adv; if (base_slot >= nslots) base_slot -= nslots;
       __syncwarp();
     }
   } else {
     // ===== epilogue: 4 warps, warp q owns TMEM lanes 32q..32q+31 =====
     const int q = warp & 3;
-    const int Gout_local = N / 8;
     const long long HWo = (long long)P.Hout * P.Wout;
     for (int it = 0; it < niter; ++it) {
-      const int buf = it & 1;
-      mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+      const int buf = NBUF == 2 ? (it & 1) : 0;
+      mbar_wait(&tmem_full[buf], (NBUF == 2 ? (it >> 1) : it) & 1);
       tc_fence_after();
       const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS;
 #pragma unroll
@@ -235,23 +254,27 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
           for (int pdh = 0; pdh < 4; ++pdh) {
             const int pd = pdh >> 1, ph = pdh & 1;
             const int zo = 2 * it + pd, yo = 2 * yi + ph, xo = 2 * xi;
-#pragma unroll
-            for (int n0 = 0; n0 < N; n0 += 8) {
-              uint32_t v0[8], v1[8];
-              tmem_ld8(tbase + ((pdh * 2 + 0) * MC + c) * N + n0, v0);
-              tmem_ld8(tbase + ((pdh * 2 + 1) * MC + c) * N + n0, v1);
+            const uint32_t cbase = tbase + (pdh * MC + c) * N;
+#pragma unroll 1
+            for (int n0 = 0; n0 < CP; n0 += 8) {
+              uint32_t ya[8], yb[8], yc[8];  // tw = 1 (even x), tw = 2 (odd x, same input), tw = 0 (odd x, input + 1)
+              tmem_ld8(cbase + n0, ya);
+              tmem_ld8(cbase + CP + n0, yb);
+              tmem_ld8(cbase + 2 * CP + n0, yc);
               tmem_ld_wait();
+              F8 r0, r1;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float a = __uint_as_float(ya[j]);
+                float bb = __uint_as_float(yb[j]) + shfl_dn(yc[j], 1);
+                a = a * sScale[n0 + j] + sShift[n0 + j];
+                bb = bb * sScale[n0 + j] + sShift[n0 + j];
+                if (P.relu) { a = fmaxf(a, 0.f); bb = fmaxf(bb, 0.f); }
+                r0.v[j] = a; r1.v[j] = bb;
+              }
               if (valid && P.n0 + n0 < P.Cout) {
                 const int go = P.out_g0 + n0 / 8;
                 const size_t off = g8_offset(b, go, zo, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
-                F8 r0, r1;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float a = __uint_as_float(v0[j]) * sScale[n0 + j] + sShift[n0 + j];
-                  float bb = __uint_as_float(v1[j]) * sScale[n0 + j] + sShift[n0 + j];
-                  if (P.relu) { a = fmaxf(a, 0.f); bb = fmaxf(bb, 0.f); }
-                  r0.v[j] = a; r1.v[j] = bb;
-                }
                 if (P.skip) {
                   F8 s0 = load8(P.skip + off), s1 = load8(P.skip + off + 8);
 #pragma unroll
@@ -273,26 +296,33 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
             yo = ty0 + ty; xo = tx0 + (tx >> 1);
             valid = !(tx & 1) && (tx >> 1) < G_::TW && yo < P.Hout && xo < P.Wout;
           }
+          const uint32_t cbase = tbase + c * N;
           if (P.plain_out) {
-            uint32_t v[8];
-            tmem_ld8(tbase + c * N, v);
+            uint32_t y0, y1, y2;
+            tmem_ld1(cbase, y0);
+            tmem_ld1(cbase + CP, y1);
+            tmem_ld1(cbase + 2 * CP, y2);
             tmem_ld_wait();
-            if (valid) reinterpret_cast<float*>(P.out)[((long long)b * P.Dout + it) * HWo + (long long)yo * P.Wout + xo] = __uint_as_float(v[0]);
+            const float v = __uint_as_float(y0) + shfl_dn(y1, 1) + shfl_dn(y2, 2);
+            if (valid) reinterpret_cast<float*>(P.out)[((long long)b * P.Dout + it) * HWo + (long long)yo * P.Wout + xo] = v;
           } else {
-#pragma unroll
-            for (int n0 = 0; n0 < N; n0 += 8) {
-              uint32_t v[8];
-              tmem_ld8(tbase + c * N + n0, v);
+#pragma unroll 1
+            for (int n0 = 0; n0 < CP; n0 += 8) {
+              uint32_t y0[8], y1[8], y2[8];
+              tmem_ld8(cbase + n0, y0);
+              tmem_ld8(cbase + CP + n0, y1);
+              tmem_ld8(cbase + 2 * CP + n0, y2);
               tmem_ld_wait();
+              F8 r;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float a = __uint_as_float(y0[j]) + shfl_dn(y1[j], 1) + shfl_dn(y2[j], 2);
+                a = a * sScale[n0 + j] + sShift[n0 + j];
+                r.v[j] = P.relu ? fmaxf(a, 0.f) : a;
+              }
               if (valid && P.n0 + n0 < P.Cout) {
                 const int go = P.out_g0 + n0 / 8;
                 const size_t off = g8_offset(b, go, it, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
-                F8 r;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float a = __uint_as_float(v[j]) * sScale[n0 + j] + sShift[n0 + j];
-                  r.v[j] = P.relu ? fmaxf(a, 0.f) : a;
-                }
                 if (P.skip) {
                   F8 s = load8(P.skip + off);
 #pragma unroll
@@ -304,7 +334,6 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
           }
         }
       }
-      (void)Gout_local;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -323,23 +352,23 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
 // host side: per-layer MMA program, weight packing, tensor maps, launch
 // ---------------------------------------------------------------------------------------------
 static int mode_of(const damvs_conv3d_desc* d) { return d->transposed ? MODE_T : (d->stride == 2 ? MODE_S2 : MODE_S1); }
-static int padded_n(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
+static int padded_c(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : 64); }
 
-struct Half { int patch, g, dy, dx, tap; };
+struct Half { int patch, g, dy, tap; };
 
 static bool build_program(int mode, int G, std::vector<StepSrc>& steps) {
   steps.clear();
+  if (G != 1 && G % 2 != 0) return false;
   auto emit = [&](int slot_rel, int cls, bool first, const Half& a, const Half& b2) {
     StepSrc s{};
     s.slot_rel = (int8_t)slot_rel; s.cls = (int8_t)cls; s.first = first ? 1 : 0;
     const Half* h[2] = {&a, &b2};
     for (int i = 0; i < 2; ++i) {
-      s.patch[i] = (int8_t)h[i]->patch; s.g[i] = (int8_t)h[i]->g; s.dy[i] = (int8_t)h[i]->dy;
-      s.dx[i] = (int8_t)h[i]->dx; s.tap[i] = (int8_t)h[i]->tap;
+      s.patch[i] = (int8_t)h[i]->patch; s.g[i] = (int8_t)h[i]->g; s.dy[i] = (int8_t)h[i]->dy; s.tap[i] = (int8_t)h[i]->tap;
     }
     steps.push_back(s);
   };
-  // halves of one (class, slot) group are emitted in increasing shared-memory offset so LBO >= 0
+  // `taps` of one (class, slot) group must be listed in increasing shared-memory offset so that LBO > 0
   auto emit_group = [&](int slot_rel, int cls, bool& first, std::vector<Half>& taps) {
     if (G % 2 == 0) {
       for (const Half& t : taps)
@@ -349,81 +378,87 @@ static bool build_program(int mode, int G, std::vector<StepSrc>& steps) {
           emit(slot_rel, cls, first, a, b2);
           first = false;
         }
-    } else {  // G == 1: pair consecutive taps; an odd tail is paired with zero weights on the next row
+    } else {  // G == 1 (Cin = 8): a K=16 MMA spans two taps; an odd tail re-reads the previous tap with zero weights
       for (size_t i = 0; i < taps.size(); i += 2) {
-        Half a = taps[i], b2;
-        if (i + 1 < taps.size()) b2 = taps[i + 1];
-        else { b2 = a; b2.dx += 1; b2.tap = -1; }
+        Half a, b2;
+        if (i + 1 < taps.size()) { a = taps[i]; b2 = taps[i + 1]; }
+        else if (i > 0) { a = taps[i - 1]; a.tap = -1; b2 = taps[i]; }
+        else return false;
         emit(slot_rel, cls, first, a, b2);
         first = false;
       }
     }
+    return true;
   };
-  if (G != 1 && G % 2 != 0) return false;
+  bool ok = true;
   if (mode == MODE_S1) {
     bool first = true;
     for (int kd = 0; kd < 3; ++kd) {
       std::vector<Half> taps;
-      for (int kh = 0; kh < 3; ++kh)
-        for (int kw = 0; kw < 3; ++kw) taps.push_back({0, 0, kh, kw, kd * 9 + kh * 3 + kw});
-      emit_group(kd, 0, first, taps);
+      for (int kh = 0; kh < 3; ++kh) taps.push_back({0, 0, kh, kd * 3 + kh});
+      ok = ok && emit_group(kd, 0, first, taps);
     }
   } else if (mode == MODE_S2) {
     bool first = true;
     for (int kd = 0; kd < 3; ++kd) {
-      std::vector<Half> taps;  // even-row patch first (lower addresses), then the odd-row patch
-      for (int kw = 0; kw < 3; ++kw) taps.push_back({0, 0, 0, kw, kd * 9 + 1 * 3 + kw});
-      for (int kw = 0; kw < 3; ++kw) taps.push_back({1, 0, 0, kw, kd * 9 + 0 * 3 + kw});
-      for (int kw = 0; kw < 3; ++kw) taps.push_back({1, 0, 1, kw, kd * 9 + 2 * 3 + kw});
-      emit_group(kd, 0, first, taps);
+      std::vector<Half> taps;  // even-row patch (kh = 1) first, then the odd-row patch (kh = 0 at row r, kh = 2 at row r+1)
+      taps.push_back({0, 0, 0, kd * 3 + 1});
+      taps.push_back({1, 0, 0, kd * 3 + 0});
+      taps.push_back({1, 0, 1, kd * 3 + 2});
+      ok = ok && emit_group(kd, 0, first, taps);
     }
   } else {
     if (G % 2) return false;
     // output o = 2*i - 1 + t: parity 0 <- (t=1, i=j); parity 1 <- (t=2, i=j), (t=0, i=j+1)
     auto dim_taps = [](int p, int (&t)[2], int (&s)[2]) { if (p == 0) { t[0] = 1; s[0] = 0; return 1; } t[0] = 2; s[0] = 0; t[1] = 0; s[1] = 1; return 2; };
     for (int pd = 0; pd < 2; ++pd)
-      for (int ph = 0; ph < 2; ++ph)
-        for (int pw = 0; pw < 2; ++pw) {
-          const int cls = pd * 4 + ph * 2 + pw;
-          bool first = true;
-          int td[2], sd[2], th[2], sh[2], tw[2], sw[2];
-          int nd = dim_taps(pd, td, sd), nh = dim_taps(ph, th, sh), nw = dim_taps(pw, tw, sw);
-          for (int a = 0; a < nd; ++a) {
-            std::vector<Half> taps;
-            for (int bq = 0; bq < nh; ++bq)
-              for (int c = 0; c < nw; ++c) taps.push_back({0, 0, sh[bq], sw[c], td[a] * 9 + th[bq] * 3 + tw[c]});
-            emit_group(sd[a], cls, first, taps);
-          }
+      for (int ph = 0; ph < 2; ++ph) {
+        const int cls = pd * 2 + ph;
+        bool first = true;
+        int td[2], sd[2], th[2], sh[2];
+        int nd = dim_taps(pd, td, sd), nh = dim_taps(ph, th, sh);
+        for (int a = 0; a < nd; ++a) {
+          std::vector<Half> taps;
+          for (int bq = 0; bq < nh; ++bq) taps.push_back({0, 0, sh[bq], td[a] * 3 + th[bq]});
+          ok = ok && emit_group(sd[a], cls, first, taps);
         }
+      }
   }
-  return (int)steps.size() <= kMaxSteps;
+  return ok && (int)steps.size() <= kMaxSteps;
 }
 
 // how many output-channel blobs a layer is split into so that weights + ring fit in shared memory
 static int n_split(int Cin, int Cout) { return (Cin >= 64 && Cout >= 64) ? 2 : 1; }
 
-static size_t blob_bytes(int nsteps, int N) { return (size_t)weights_offset(nsteps) + (size_t)nsteps * 2 * N * 16; }
+static size_t blob_bytes(int nsteps, int CP) { return (size_t)weights_offset(nsteps) + (size_t)nsteps * 2 * 3 * CP * 16; }
 
 size_t conv3d_tc_packed_bytes(const damvs_conv3d_desc* d) {
   std::vector<StepSrc> steps;
   if (!build_program(mode_of(d), d->Cin / 8, steps)) return 0;
   int split = n_split(d->Cin, d->Cout);
-  int N = padded_n(d->Cout / split);
-  return (blob_bytes((int)steps.size(), N) + 255) / 256 * 256 * split;
+  int CP = padded_c(d->Cout / split);
+  return (blob_bytes((int)steps.size(), CP) + 255) / 256 * 256 * split;
 }
 
+// B operand of step s: [2 K-halves][N = 3*CP rows][8 channels] bf16; row n = j*CP + co where j is the folded
+// w tap (conv: kw = j; transposed: tw = {1, 2, 0}[j]).
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, uint8_t* __restrict__ blob, int Cin, int Cout, int co_end,
-                                      int transposed, int N, int n0, int nsteps) {
+                                      int transposed, int CP, int n0, int nsteps) {
   const StepSrc* steps = reinterpret_cast<const StepSrc*>(blob + steps_offset());
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(blob + weights_offset(nsteps));
+  const int N = 3 * CP;
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [nsteps][2][N][8]
   if (i >= nsteps * 2 * N * 8) return;
-  int j = i & 7, n = (i >> 3) % N, h = (i / (8 * N)) & 1, s = i / (16 * N);
+  int j8 = i & 7, n = (i >> 3) % N, h = (i / (8 * N)) & 1, s = i / (16 * N);
   StepSrc st = steps[s];
-  int co = n0 + n, ci = st.g[h] * 8 + j, tap = st.tap[h];
+  const int jw = n / CP, col = n - jw * CP;
+  const int kw = transposed ? (jw == 0 ? 1 : (jw == 1 ? 2 : 0)) : jw;
+  int co = n0 + col, ci = st.g[h] * 8 + j8, tap2 = st.tap[h];
   float v = 0.f;
-  if (tap >= 0 && co < co_end)
+  if (tap2 >= 0 && co < co_end) {
+    const int tap = tap2 * 3 + kw;
     v = transposed ? w[((size_t)ci * Cout + co) * 27 + tap] : w[((size_t)co * Cin + ci) * 27 + tap];
+  }
   dst[i] = __float2bfloat16_rn(v);
 }
 
@@ -434,19 +469,19 @@ int conv3d_tc_pack(const damvs_conv3d_desc* d, const float* weight, void* packed
   if (d->Cout > 64 && !d->plain_out) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cout=%d > 64", d->Cout);
   const int split = n_split(d->Cin, d->Cout);
   const int cper = d->Cout / split;
-  const int N = padded_n(cper);
+  const int CP = padded_c(cper);
   const int nsteps = (int)steps.size();
-  const size_t bb = (blob_bytes(nsteps, N) + 255) / 256 * 256;
+  const size_t bb = (blob_bytes(nsteps, CP) + 255) / 256 * 256;
   for (int k = 0; k < split; ++k) {
     uint8_t* blob = (uint8_t*)packed + k * bb;
     PackedHeader h{};
-    h.magic = kMagic; h.mode = mode; h.Cin = d->Cin; h.Cout = d->Cout; h.N = N; h.nsteps = nsteps;
-    h.ncls = mode == MODE_T ? 8 : 1; h.n0 = k * cper; h.blob_bytes = (int)bb; h.nblobs = split;
+    h.magic = kMagic; h.mode = mode; h.Cin = d->Cin; h.Cout = d->Cout; h.CP = CP; h.nsteps = nsteps;
+    h.ncls = mode == MODE_T ? 4 : 1; h.n0 = k * cper; h.blob_bytes = (int)bb; h.nblobs = split;
     DAMVS_CUDA_OK(cudaMemcpyAsync(blob, &h, sizeof(h), cudaMemcpyHostToDevice, st));
     DAMVS_CUDA_OK(cudaMemcpyAsync(blob + steps_offset(), steps.data(), nsteps * sizeof(StepSrc), cudaMemcpyHostToDevice, st));
-    int total = nsteps * 2 * N * 8;
+    int total = nsteps * 2 * 3 * CP * 8;
     // the blob computes channels [n0, n0 + cper); rows beyond that are zero padding
-    pack_weight_tc_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, blob, d->Cin, d->Cout, (k + 1) * cper, d->transposed, N,
+    pack_weight_tc_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, blob, d->Cin, d->Cout, (k + 1) * cper, d->transposed, CP,
                                                               k * cper, nsteps);
     DAMVS_LAUNCH_OK("pack_weight_tc kernel");
   }
@@ -487,14 +522,16 @@ static int make_map(CUtensorMap* m, const void* base, int BG, int D, int H, int 
   return DAMVS_OK;
 }
 
-static size_t smem_need(int mode, int G, int N, int MC, int nsteps) {
+static size_t slot_bytes(int mode, int G, int MC) {
   const int rows = mode == MODE_S1 ? 4 * MC + 2 : (mode == MODE_T ? 4 * MC + 1 : 8 * MC + 1);
-  const size_t slot_stride = (size_t)G * rows * kP * 16 + 128;
-  return kSlots * slot_stride + (size_t)nsteps * 2 * N * 16 + 2 * N * sizeof(float) +
-         (2 * kSlots + 4) * sizeof(uint64_t) + 16;
+  return (size_t)G * rows * kP * 16;
 }
+static size_t fixed_smem(int CP, int nsteps) {
+  return (size_t)nsteps * 2 * 3 * CP * 16 + 2 * CP * sizeof(float) + (2 * kMaxSlots + 4) * sizeof(uint64_t) + 16;
+}
+constexpr size_t kSmemBudget = 227 * 1024;
 
-template <int MODE, int N, int MC>
+template <int MODE, int CP, int MC>
 static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, const std::vector<StepSrc>& steps, cudaStream_t st) {
   using G_ = Geo<MODE>;
   const int G = d->Cin / 8;
@@ -507,9 +544,9 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
       uint32_t off[2];
       for (int h = 0; h < 2; ++h) {
         const int rows = src.patch[h] ? G_::rows1(MC) : G_::rows0(MC);
-        off[h] = (src.patch[h] ? patch0_bytes : 0) + ((src.g[h] * rows + src.dy[h]) * kP + src.dx[h]) * 16;
+        off[h] = (src.patch[h] ? patch0_bytes : 0) + ((src.g[h] * rows + src.dy[h]) * kP) * 16;
       }
-      if (off[1] < off[0] || ((off[1] - off[0]) >> 4) >= (1u << 14) || (off[0] >> 4) >= (1u << 14))
+      if (off[1] <= off[0] || ((off[1] - off[0]) >> 4) >= (1u << 14) || (off[0] >> 4) >= (1u << 14))
         return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: step %d has an unencodable operand offset", s);
       P.prog[s].a_word = (off[0] >> 4) | (((off[1] - off[0]) >> 4) << 16);
       P.prog[s].info = (uint32_t)src.slot_rel | ((uint32_t)src.cls << 2) | (src.first ? 0x80u : 0u);
@@ -524,8 +561,18 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
     if ((rc = make_map(&m0, in, d->B * G, d->Din, d->Hin, d->Win, 0, 1, G_::rows0(MC), G))) return rc;
     m1 = m0;
   }
-  const size_t smem = smem_need(MODE, G, N, MC, nsteps);
-  auto kern = conv3d_tc_kernel<MODE, N, MC>;
+  // ring depth: TMA runs ahead of the MMAs by nslots - span planes
+  const size_t sb = slot_bytes(MODE, G, MC), fx = fixed_smem(CP, nsteps);
+  int nslots = (int)((kSmemBudget - fx) / sb);
+  const int nplanes = (P.niter - 1) * G_::adv + G_::span;
+  if (nslots > kMaxSlots) nslots = kMaxSlots;
+  if (nslots > nplanes) nslots = nplanes;
+  if (nslots < G_::span + 1 && nslots < nplanes) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: ring does not fit");
+  // leave room for a second CTA per SM when a deep ring is not needed
+  while (nslots > G_::span + 2 && fx + (size_t)nslots * sb > kSmemBudget / 2) --nslots;
+  P.nslots = nslots;
+  const size_t smem = fx + (size_t)nslots * sb;
+  auto kern = conv3d_tc_kernel<MODE, CP, MC>;
   DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int TH = 4 * MC;
   const int tiles_h = MODE == MODE_T ? d->Hin : P.Hout, tiles_w = MODE == MODE_T ? d->Win : P.Wout;
@@ -535,14 +582,26 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   return DAMVS_OK;
 }
 
-// largest M-chunk count (tile height 4*MC rows) whose ring + weights fit in shared memory and TMEM
-static int pick_mc(int mode, int G, int N, int nsteps, int tile_rows_avail) {
-  const int cap = mode == MODE_T ? 32 / N : (N == 64 ? 2 : 4);  // T: 8 classes * MC * N * 2 buffers <= 512 columns
+static bool mc_fits(int mode, int G, int CP, int nsteps, int mc) {
+  const int ncls = mode == MODE_T ? 4 : 1, span = mode == MODE_T ? 2 : 3;
+  const int acc = ncls * mc * 3 * CP;
+  if (acc > 512) return false;
+  // taller tiles only while the double-buffered accumulator stays within 256 TMEM columns (two CTAs per SM)
+  if (mc > 1 && 2 * acc > 256) return false;
+  return fixed_smem(CP, nsteps) + (size_t)(span + 1) * slot_bytes(mode, G, mc) <= kSmemBudget;
+}
+
+// tile height (4*MC rows): the largest that fits shared memory / TMEM and still yields >= 2 CTAs per SM;
+// when there is not enough work for that at any height, the smallest tile (most CTAs)
+static int pick_mc(int mode, int G, int CP, int nsteps, int tile_rows, int tile_cols, int B) {
+  const int TW = mode == MODE_S1 ? 30 : (mode == MODE_T ? 31 : 15);
   for (int mc = 4; mc >= 1; mc >>= 1) {
-    if (mc > cap) continue;
-    if (mc > 1 && 4 * (mc / 2) >= tile_rows_avail) continue;      // do not pad a short volume with empty tile rows
-    if (smem_need(mode, G, N, mc, nsteps) <= 227 * 1024) return mc;
+    if (!mc_fits(mode, G, CP, nsteps, mc)) continue;
+    const long long ctas = (long long)((tile_cols + TW - 1) / TW) * ((tile_rows + 4 * mc - 1) / (4 * mc)) * B;
+    if (ctas >= 2 * 148) return mc;
   }
+  for (int mc = 1; mc <= 4; mc <<= 1)
+    if (mc_fits(mode, G, CP, nsteps, mc)) return mc;
   return 0;
 }
 
@@ -558,7 +617,8 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
     return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: stride-2 needs even input extents");
   const int split = n_split(d->Cin, d->Cout);
   const int cper = d->Cout / split;
-  const int N = padded_n(cper);
+  const int CP = padded_c(cper);
+  if (mode == MODE_T && CP > 32) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: transposed Cout=%d > 32", d->Cout);
   TcParams P{};
   P.scale = scale; P.shift = shift; P.skip = (const __nv_bfloat16*)skip; P.out = out;
   P.B = d->B; P.G = G; P.Din = d->Din; P.Hin = d->Hin; P.Win = d->Win;
@@ -567,24 +627,24 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
   P.out_G = d->plain_out ? 1 : d->Cout / 8; P.relu = d->relu; P.plain_out = d->plain_out;
   std::vector<StepSrc> steps;
   if (!build_program(mode, G, steps)) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: no program for Cin=%d", d->Cin);
-  const size_t bb = (blob_bytes((int)steps.size(), N) + 255) / 256 * 256;
+  const int nsteps = (int)steps.size();
+  const size_t bb = (blob_bytes(nsteps, CP) + 255) / 256 * 256;
+  const int mc = pick_mc(mode, G, CP, nsteps, mode == MODE_T ? d->Hin : P.Hout, mode == MODE_T ? d->Win : P.Wout, d->B);
+  if (mc == 0) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cin=%d Cout=%d does not fit in shared memory", d->Cin, d->Cout);
   for (int k = 0; k < split; ++k) {
     P.blob = (const uint8_t*)packed + k * bb;
     P.n0 = k * cper; P.out_g0 = (k * cper) / 8; P.Cout = d->plain_out ? 1 : (k + 1) * cper;
     int rc = -1;
-    const int nsteps = (int)steps.size();
-    const int mc = pick_mc(mode, G, N, nsteps, mode == MODE_T ? d->Hin : P.Hout);
-    if (mc == 0) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cin=%d Cout=%d does not fit in shared memory", d->Cin, d->Cout);
-#define GO(MODE_, N_, MC_) if (mode == MODE_ && N == N_ && mc == MC_) rc = launch_one<MODE_, N_, MC_>(d, P, in, steps, st)
+#define GO(MODE_, CP_, MC_) if (mode == MODE_ && CP == CP_ && mc == MC_) rc = launch_one<MODE_, CP_, MC_>(d, P, in, steps, st)
     GO(MODE_S1, 16, 4); GO(MODE_S1, 16, 2); GO(MODE_S1, 16, 1);
-    GO(MODE_S1, 32, 4); GO(MODE_S1, 32, 2); GO(MODE_S1, 32, 1);
-    GO(MODE_S1, 64, 2); GO(MODE_S1, 64, 1);
+    GO(MODE_S1, 32, 2); GO(MODE_S1, 32, 1);
+    GO(MODE_S1, 64, 1);
     GO(MODE_S2, 16, 4); GO(MODE_S2, 16, 2); GO(MODE_S2, 16, 1);
-    GO(MODE_S2, 32, 4); GO(MODE_S2, 32, 2); GO(MODE_S2, 32, 1);
-    GO(MODE_S2, 64, 2); GO(MODE_S2, 64, 1);
+    GO(MODE_S2, 32, 2); GO(MODE_S2, 32, 1);
+    GO(MODE_S2, 64, 1);
     GO(MODE_T, 16, 2); GO(MODE_T, 16, 1); GO(MODE_T, 32, 1);
-    if (rc == -1) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: no kernel for mode=%d N=%d MC=%d", mode, N, mc);
 #undef GO
+    if (rc == -1) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: no kernel for mode=%d CP=%d MC=%d", mode, CP, mc);
     if (rc) return rc;
   }
   return DAMVS_OK;
