@@ -33,6 +33,8 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
 // epilogue (TMEM -> registers -> kw combine -> BN affine / ReLU / skip -> 16-byte stores).
 // Accumulators are double buffered in TMEM so the epilogue of plane z overlaps the MMAs of plane z+1.
+#include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -60,11 +62,6 @@ struct PackedHeader {  // 64 bytes
   int32_t mode, Cin, Cout, CP, nsteps, ncls, n0;  // n0: first output channel this blob computes
   int32_t blob_bytes, nblobs, pad[6];
 };
-// Launch-time form of a step, passed in the kernel parameter (constant) space so the MMA issuer reads it
-// with uniform loads: a_word = (A offset from the slot base)>>4 | (LBO>>4)<<16, info = slot_rel | cls<<2 | first<<7.
-struct StepRt {
-  uint32_t a_word, info;
-};
 
 struct TcParams {
   const uint8_t* blob;  // PackedHeader + StepSrc[nsteps] (padded to 16 B) + weights
@@ -75,7 +72,7 @@ struct TcParams {
   int B, G, Din, Hin, Win, Dout, Hout, Wout;
   int out_G, out_g0;  // output volume's group count and first group written by this launch
   int n0, Cout, relu, plain_out, niter, nsteps, nslots;
-  StepRt prog[kMaxSteps];
+  unsigned long long* trace;  // development aid: per-CTA event timestamps (null in production)
 };
 
 __host__ __device__ inline int steps_offset() { return (int)sizeof(PackedHeader); }
@@ -92,9 +89,103 @@ struct Geo {
   __host__ __device__ static constexpr int rows1(int MC) { return MODE == MODE_S2 ? 4 * MC + 1 : 0; }
 };
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot_)                                                                                              \
+  do {                                                                                                            \
+    if (P.trace) P.trace[((size_t)(blockIdx.y * gridDim.x + blockIdx.x)) * 64 + (slot_)] = gtime();                \
+  } while (0)
+
 __device__ __forceinline__ float shfl_dn(uint32_t v, int d) { return __uint_as_float(__shfl_down_sync(0xffffffffu, v, d)); }
 
-template <int MODE, int CP, int MC>
+
+// ---------------------------------------------------------------------------------------------
+// The per-iteration MMA program as straight-line code: every operand offset is a compile-time
+// constant (MODE, G = Cin/8 and MC are template parameters), only the three plane-slot bases are
+// run-time (uniform) values.  The order of the steps is the order build_program() emits on the host,
+// which is also the order of the packed B operands.
+// ---------------------------------------------------------------------------------------------
+template <int N, int MC>
+__device__ __forceinline__ void issue_step(bool leader, uint32_t so, uint32_t a_off16, uint32_t lbo16, uint32_t b_base16, int step,
+                                           uint32_t dcol, uint32_t acc) {
+  constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
+  constexpr uint32_t IDESC = idesc_bf16_m128(N);
+  const uint64_t bdesc = ((uint64_t)DESC_HI << 32) | ((b_base16 + step * (2 * N)) | ((uint32_t)N << 16));  // LBO = N*16 bytes
+#pragma unroll
+  for (int c = 0; c < MC; ++c) {
+    const uint64_t adesc = ((uint64_t)DESC_HI << 32) | ((so + a_off16 + c * 128) | (lbo16 << 16));
+    if (leader) mma_bf16_ss(dcol + c * N, adesc, bdesc, IDESC, acc);
+  }
+}
+
+template <int MODE, int CP, int MC, int G>
+__device__ __forceinline__ void issue_iteration(bool leader, uint32_t so0, uint32_t so1, uint32_t so2, uint32_t b_base16, uint32_t dbase) {
+  using G_ = Geo<MODE>;
+  constexpr int N = 3 * CP;
+  constexpr int R0 = G_::rows0(MC), R1 = G_::rows1(MC);
+  constexpr uint32_t P0_16 = (uint32_t)G * R0 * kP;  // patch-0 size in 16-byte units
+  int step = 0;
+  if (MODE == MODE_S1) {
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const uint32_t so = kd == 0 ? so0 : (kd == 1 ? so1 : so2);
+      if (G == 1) {  // (kh0, kh1), (kh1 with zero weights, kh2)
+        issue_step<N, MC>(leader, so, 0, kP, b_base16, step++, dbase, kd == 0 ? 0u : 1u);
+        issue_step<N, MC>(leader, so, kP, kP, b_base16, step++, dbase, 1u);
+      } else {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+          for (int gp = 0; gp < G / 2; ++gp)
+            issue_step<N, MC>(leader, so, (uint32_t)((2 * gp * R0 + kh) * kP), (uint32_t)(R0 * kP), b_base16, step++, dbase,
+                              (kd == 0 && kh == 0 && gp == 0) ? 0u : 1u);
+      }
+    }
+  } else if (MODE == MODE_S2) {
+#pragma unroll
+    for (int kd = 0; kd < 3; ++kd) {
+      const uint32_t so = kd == 0 ? so0 : (kd == 1 ? so1 : so2);
+      if (G == 1) {  // (E row, O row r), (O row r with zero weights, O row r+1)
+        issue_step<N, MC>(leader, so, 0, P0_16, b_base16, step++, dbase, kd == 0 ? 0u : 1u);
+        issue_step<N, MC>(leader, so, P0_16, kP, b_base16, step++, dbase, 1u);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 3; ++t)  // E (kh=1), O row r (kh=0), O row r+1 (kh=2)
+#pragma unroll
+          for (int gp = 0; gp < G / 2; ++gp) {
+            const uint32_t off = t == 0 ? (uint32_t)(2 * gp * R0 * kP) : P0_16 + (uint32_t)((2 * gp * R1 + (t - 1)) * kP);
+            issue_step<N, MC>(leader, so, off, (uint32_t)((t == 0 ? R0 : R1) * kP), b_base16, step++, dbase,
+                              (kd == 0 && t == 0 && gp == 0) ? 0u : 1u);
+          }
+      }
+    }
+  } else {
+    // parity 0 <- one tap (shift 0); parity 1 <- two taps (shift 0, then shift 1)
+#pragma unroll
+    for (int pd = 0; pd < 2; ++pd)
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        const uint32_t dcol = dbase + (pd * 2 + ph) * MC * N;
+        bool first = true;
+#pragma unroll
+        for (int a = 0; a <= pd; ++a) {        // d taps: shift a
+          const uint32_t so = a == 0 ? so0 : so1;
+#pragma unroll
+          for (int bq = 0; bq <= ph; ++bq)     // h taps: shift bq
+#pragma unroll
+            for (int gp = 0; gp < G / 2; ++gp) {
+              issue_step<N, MC>(leader, so, (uint32_t)((2 * gp * R0 + bq) * kP), (uint32_t)(R0 * kP), b_base16, step++, dcol, first ? 0u : 1u);
+              first = false;
+            }
+        }
+      }
+  }
+}
+
+template <int MODE, int CP, int MC, int G>
 __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0,
                                                         const __grid_constant__ CUtensorMap map1,
                                                         const __grid_constant__ TcParams P) {
@@ -109,7 +200,6 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
   constexpr uint32_t IDESC = idesc_bf16_m128(N);
 
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int G = P.G;
   const int patch0_bytes = G * G_::rows0(MC) * kP * 16;
   const int patch1_bytes = G * G_::rows1(MC) * kP * 16;
   const int slot_stride = patch0_bytes + patch1_bytes;
@@ -137,6 +227,7 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
   const int ty0 = blockIdx.y * TH;     // tile origin (output coords for S1/S2, input coords for T)
   const int tx0 = blockIdx.x * G_::TW;
 
+  if (threadIdx.x == 0) TRACE(0);
   // ---- one-time setup ------------------------------------------------------------------------
   {
     const uint4* wsrc = reinterpret_cast<const uint4*>(P.blob + weights_offset(nsteps));
@@ -164,6 +255,7 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int niter = P.niter;
+  if (threadIdx.x == 0) TRACE(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -192,7 +284,6 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
     const bool leader = elect_one();
     const uint32_t a_base16 = smem_u32(sA) >> 4, b_base16 = smem_u32(sB) >> 4;
     const uint32_t slot16 = (uint32_t)slot_stride >> 4;
-    constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
     int wait_slot = 0, wait_round = 0, next_wait = 0;       // full-barrier cursor
     int base_slot = 0;                                       // slot of the first plane of this iteration
     for (int it = 0; it < niter; ++it) {
@@ -202,28 +293,18 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
         ++next_wait;
         if (++wait_slot == nslots) { wait_slot = 0; ++wait_round; }
       }
+      if (leader && it < 12) TRACE(4 + it);
       const int buf = NBUF == 2 ? (it & 1) : 0;
       if (it >= NBUF) mbar_wait(&tmem_empty[buf], (NBUF == 2 ? ((it >> 1) - 1) : (it - 1)) & 1);
       tc_fence_after();
+      if (leader && it < 12) TRACE(16 + it);
       const uint32_t dbase = tmem_base + buf * ACC_COLS;
       int s1 = base_slot + 1; if (s1 >= nslots) s1 -= nslots;
       int s2 = base_slot + 2; if (s2 >= nslots) s2 -= nslots;
       const uint32_t so0 = a_base16 + base_slot * slot16;
       const uint32_t so1 = a_base16 + s1 * slot16;
       const uint32_t so2 = a_base16 + s2 * slot16;
-#pragma unroll 1
-      for (int s = 0; s < nsteps; ++s) {
-        const StepRt st = P.prog[s];
-        const uint32_t rel = st.info & 3u, cls = (st.info >> 2) & 15u, acc = (st.info >> 7) & 1u ? 0u : 1u;
-        const uint32_t a_lo = st.a_word + (rel == 0 ? so0 : (rel == 1 ? so1 : so2));
-        const uint32_t b_lo = (b_base16 + s * (2 * N)) | ((uint32_t)N << 16);  // LBO = N*16 bytes
-        const uint64_t bdesc = ((uint64_t)DESC_HI << 32) | b_lo;
-#pragma unroll
-        for (int c = 0; c < MC; ++c) {
-          const uint64_t adesc = ((uint64_t)DESC_HI << 32) | (a_lo + c * 128);
-          if (leader) mma_bf16_ss(dbase + (cls * MC + c) * N, adesc, bdesc, IDESC, acc);
-        }
-      }
+      issue_iteration<MODE, CP, MC, G>(leader, so0, so1, so2, b_base16, dbase);
       if (leader) {
         mma_commit(&tmem_full[buf]);
 #pragma unroll
@@ -243,6 +324,7 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
       const int buf = NBUF == 2 ? (it & 1) : 0;
       mbar_wait(&tmem_full[buf], (NBUF == 2 ? (it >> 1) : it) & 1);
       tc_fence_after();
+      if (warp == 2 && lane == 0 && it < 12) TRACE(28 + it);
       const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS;
 #pragma unroll
       for (int c = 0; c < MC; ++c) {
@@ -337,6 +419,7 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      if (warp == 2 && lane == 0 && it < 12) TRACE(40 + it);
     }
   }
 
@@ -346,6 +429,7 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 32) TRACE(2);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -531,27 +615,11 @@ static size_t fixed_smem(int CP, int nsteps) {
 }
 constexpr size_t kSmemBudget = 227 * 1024;
 
-template <int MODE, int CP, int MC>
+template <int MODE, int CP, int MC, int G>
 static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, const std::vector<StepSrc>& steps, cudaStream_t st) {
   using G_ = Geo<MODE>;
-  const int G = d->Cin / 8;
   const int nsteps = (int)steps.size();
-  {
-    const int patch0_bytes = G * G_::rows0(MC) * kP * 16;
-    P.nsteps = nsteps;
-    for (int s = 0; s < nsteps; ++s) {
-      const StepSrc& src = steps[s];
-      uint32_t off[2];
-      for (int h = 0; h < 2; ++h) {
-        const int rows = src.patch[h] ? G_::rows1(MC) : G_::rows0(MC);
-        off[h] = (src.patch[h] ? patch0_bytes : 0) + ((src.g[h] * rows + src.dy[h]) * kP) * 16;
-      }
-      if (off[1] <= off[0] || ((off[1] - off[0]) >> 4) >= (1u << 14) || (off[0] >> 4) >= (1u << 14))
-        return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: step %d has an unencodable operand offset", s);
-      P.prog[s].a_word = (off[0] >> 4) | (((off[1] - off[0]) >> 4) << 16);
-      P.prog[s].info = (uint32_t)src.slot_rel | ((uint32_t)src.cls << 2) | (src.first ? 0x80u : 0u);
-    }
-  }
+  P.nsteps = nsteps;
   CUtensorMap m0, m1;
   int rc;
   if (MODE == MODE_S2) {
@@ -572,11 +640,39 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   while (nslots > G_::span + 2 && fx + (size_t)nslots * sb > kSmemBudget / 2) --nslots;
   P.nslots = nslots;
   const size_t smem = fx + (size_t)nslots * sb;
-  auto kern = conv3d_tc_kernel<MODE, CP, MC>;
+  auto kern = conv3d_tc_kernel<MODE, CP, MC, G>;
   DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int TH = 4 * MC;
   const int tiles_h = MODE == MODE_T ? d->Hin : P.Hout, tiles_w = MODE == MODE_T ? d->Win : P.Wout;
   dim3 grid((tiles_w + G_::TW - 1) / G_::TW, (tiles_h + TH - 1) / TH, d->B);
+  const char* tr = getenv("DAMVS_TC_TRACE");
+  if (tr) {  // development aid: timestamps of a few CTAs, printed to stderr (synchronises!)
+    const size_t n = (size_t)grid.x * grid.y * 64;
+    unsigned long long* dbuf;
+    cudaMalloc(&dbuf, n * 8);
+    cudaMemset(dbuf, 0, n * 8);
+    P.trace = dbuf;
+    kern<<<grid, 192, smem, st>>>(m0, m1, P);
+    cudaStreamSynchronize(st);
+    std::vector<unsigned long long> h(n);
+    cudaMemcpy(h.data(), dbuf, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dbuf);
+    P.trace = nullptr;
+    unsigned long long t0 = ~0ull, t1 = 0;
+    for (size_t c = 0; c < n / 64; ++c) { if (h[c * 64]) t0 = std::min(t0, h[c * 64]); t1 = std::max(t1, h[c * 64 + 2]); }
+    fprintf(stderr, "[tc trace] mode %d CP %d MC %d G %d grid %ux%u niter %d nslots %d smem %zu: kernel span %.1f us\n", MODE, CP, MC, G, grid.x,
+            grid.y, P.niter, nslots, smem, (t1 - t0) / 1e3);
+    const size_t picks[3] = {0, n / 64 / 2, n / 64 - 1};
+    for (size_t pi = 0; pi < 3; ++pi) {
+      const unsigned long long* e = &h[picks[pi] * 64];
+      fprintf(stderr, "  cta %zu: start +%.1f us, setup %.2f, life %.2f us | iter: ", picks[pi], (e[0] - t0) / 1e3, (e[1] - e[0]) / 1e3, (e[2] - e[0]) / 1e3);
+      for (int it = 0; it < P.niter && it < 12; ++it)
+        fprintf(stderr, "[%d mma_rdy %.2f acc_free %.2f epi_start %.2f epi_end %.2f] ", it, (e[4 + it] - e[0]) / 1e3, (e[16 + it] - e[0]) / 1e3,
+                (e[28 + it] - e[0]) / 1e3, (e[40 + it] - e[0]) / 1e3);
+      fprintf(stderr, "\n");
+    }
+    return DAMVS_OK;
+  }
   kern<<<grid, 192, smem, st>>>(m0, m1, P);
   DAMVS_LAUNCH_OK("conv3d_tc kernel");
   return DAMVS_OK;
@@ -635,16 +731,22 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
     P.blob = (const uint8_t*)packed + k * bb;
     P.n0 = k * cper; P.out_g0 = (k * cper) / 8; P.Cout = d->plain_out ? 1 : (k + 1) * cper;
     int rc = -1;
-#define GO(MODE_, CP_, MC_) if (mode == MODE_ && CP == CP_ && mc == MC_) rc = launch_one<MODE_, CP_, MC_>(d, P, in, steps, st)
-    GO(MODE_S1, 16, 4); GO(MODE_S1, 16, 2); GO(MODE_S1, 16, 1);
-    GO(MODE_S1, 32, 2); GO(MODE_S1, 32, 1);
-    GO(MODE_S1, 64, 1);
-    GO(MODE_S2, 16, 4); GO(MODE_S2, 16, 2); GO(MODE_S2, 16, 1);
-    GO(MODE_S2, 32, 2); GO(MODE_S2, 32, 1);
-    GO(MODE_S2, 64, 1);
-    GO(MODE_T, 16, 2); GO(MODE_T, 16, 1); GO(MODE_T, 32, 1);
+#define GO(MODE_, CP_, MC_, G_)                                   \
+  if (mode == MODE_ && CP == CP_ && mc == MC_ && G == G_) rc = launch_one<MODE_, CP_, MC_, G_>(d, P, in, steps, st)
+    // the layer shapes of CostRegNet with base_channels 8 (reference models/module.py:513-530)
+    GO(MODE_S1, 16, 2, 1); GO(MODE_S1, 16, 1, 1);   // conv0 (stage 3), prob
+    GO(MODE_S1, 16, 2, 2); GO(MODE_S1, 16, 1, 2);   // conv0 (stage 2), conv2
+    GO(MODE_S1, 16, 2, 4); GO(MODE_S1, 16, 1, 4);   // conv0 (stage 1)
+    GO(MODE_S1, 32, 1, 4);                           // conv4
+    GO(MODE_S1, 32, 1, 8);                           // conv6 (two output halves)
+    GO(MODE_S2, 16, 2, 1); GO(MODE_S2, 16, 1, 1);   // conv1
+    GO(MODE_S2, 32, 1, 2);                           // conv3
+    GO(MODE_S2, 64, 1, 4);                           // conv5
+    GO(MODE_T, 32, 1, 8);                            // conv7
+    GO(MODE_T, 16, 2, 4); GO(MODE_T, 16, 1, 4);     // conv9
+    GO(MODE_T, 16, 2, 2); GO(MODE_T, 16, 1, 2);     // conv11
 #undef GO
-    if (rc == -1) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: no kernel for mode=%d CP=%d MC=%d", mode, CP, mc);
+    if (rc == -1) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: no kernel for mode=%d Cin=%d CP=%d MC=%d", mode, d->Cin, CP, mc);
     if (rc) return rc;
   }
   return DAMVS_OK;

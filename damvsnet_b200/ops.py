@@ -60,14 +60,21 @@ def conv_impl_for(cin: int, cout: int, stride: int, transposed: bool) -> int:
 
 
 def tc_supported(cin: int, cout: int, stride: int, transposed: bool) -> bool:
-    """Layer shapes conv3d_tc.cu covers (bf16 in/out): Cin = 8 or a multiple of 16, Cout <= 64
-    (<= 32 for the transposed conv, whose 8 parity classes share the 512 TMEM columns)."""
+    """Layer shapes conv3d_tc.cu has kernels for (bf16 in/out): the CostRegNet layers with base_channels 8
+    (reference models/module.py:513-530) -- see the dispatch table in conv3d_tc_launch.  Anything else runs
+    on the direct kernel."""
+    def cp(c):
+        return 16 if c <= 16 else (32 if c <= 32 else 64)
     g = cin // 8
-    if cin % 8 or not (g == 1 or g % 2 == 0) or g > 8:
+    if cin % 8 or cout > 64:
         return False
     if transposed:
-        return g % 2 == 0 and cout <= 32
-    return cout <= 64
+        return (g, cp(cout)) in ((8, 32), (4, 16), (2, 16))
+    if stride == 2:
+        return (g, cp(cout)) in ((1, 16), (2, 32), (4, 64))
+    if cin == 64 and cout == 64:
+        return True                      # two launches of 32 output channels
+    return (g, cp(cout)) in ((1, 16), (2, 16), (4, 16), (4, 32), (8, 32))
 
 
 # --------------------------------------------------------------------------
