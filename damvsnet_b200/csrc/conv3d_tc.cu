@@ -30,7 +30,7 @@
 // classes x the w-parity pair folded into N, each class a 1/2/4-tap sub-convolution of the same
 // input patch with its own TMEM accumulator).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 =
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-9 =
 // epilogue (TMEM -> registers -> kw combine -> BN affine / ReLU / skip -> 16-byte stores).
 // Accumulators are double buffered in TMEM so the epilogue of plane z overlaps the MMAs of plane z+1.
 #include <algorithm>
@@ -186,7 +186,7 @@ __device__ __forceinline__ void issue_iteration(bool leader, uint32_t so0, uint3
 }
 
 template <int MODE, int CP, int MC, int G>
-__global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0,
+__global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0,
                                                         const __grid_constant__ CUtensorMap map1,
                                                         const __grid_constant__ TcParams P) {
   using G_ = Geo<MODE>;
@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
   if (threadIdx.x == 0) {
     for (int i = 0; i < nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4); mbar_init(&tmem_empty[1], 4);
+    mbar_init(&tmem_empty[0], 8); mbar_init(&tmem_empty[1], 8);
     fence_barrier_init();
     tma_prefetch_desc(&map0);
     if (MODE == MODE_S2) tma_prefetch_desc(&map1);
@@ -317,68 +317,100 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
       __syncwarp();
     }
   } else {
-    // ===== epilogue: 4 warps, warp q owns TMEM lanes 32q..32q+31 =====
-    const int q = warp & 3;
+    // ===== epilogue: 8 warps; warp w owns TMEM lanes 32*(w%4).., the two warps of a lane quarter split the
+    // work units (chunks, or channel groups, or parity classes) of an iteration between them =====
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    constexpr int CPG = CP / 8;
+    const int ngroups = P.plain_out ? 1 : min(CPG, (P.Cout - P.n0 + 7) / 8);   // real (non-padding) channel groups
     const long long HWo = (long long)P.Hout * P.Wout;
     for (int it = 0; it < niter; ++it) {
       const int buf = NBUF == 2 ? (it & 1) : 0;
-      mbar_wait(&tmem_full[buf], (NBUF == 2 ? (it >> 1) : it) & 1);
-      tc_fence_after();
-      if (warp == 2 && lane == 0 && it < 12) TRACE(28 + it);
       const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS;
+      if (MODE == MODE_T) {
+        // units: (class pdh in {2*half, 2*half+1}) x chunk x group; each unit = two adjacent output voxels (x parity)
+        constexpr int U = 2 * MC * CPG;
+        uint4 sk[U][2];
+        size_t offs[U];
+        bool valid[MC];
 #pragma unroll
-      for (int c = 0; c < MC; ++c) {
-        const int ty = c * 4 + q, tx = lane;
-        if (MODE == MODE_T) {
-          const int yi = ty0 + ty, xi = tx0 + tx;
-          const bool valid = tx < G_::TW && yi < P.Hin && xi < P.Win;
-#pragma unroll 1
-          for (int pdh = 0; pdh < 4; ++pdh) {
-            const int pd = pdh >> 1, ph = pdh & 1;
-            const int zo = 2 * it + pd, yo = 2 * yi + ph, xo = 2 * xi;
-            const uint32_t cbase = tbase + (pdh * MC + c) * N;
-#pragma unroll 1
-            for (int n0 = 0; n0 < CP; n0 += 8) {
-              uint32_t ya[8], yb[8], yc[8];  // tw = 1 (even x), tw = 2 (odd x, same input), tw = 0 (odd x, input + 1)
-              tmem_ld8(cbase + n0, ya);
-              tmem_ld8(cbase + CP + n0, yb);
-              tmem_ld8(cbase + 2 * CP + n0, yc);
-              tmem_ld_wait();
-              F8 r0, r1;
+        for (int c = 0; c < MC; ++c) {
+          const int yi = ty0 + c * 4 + q, xi = tx0 + lane;
+          valid[c] = lane < G_::TW && yi < P.Hin && xi < P.Win;
+        }
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float a = __uint_as_float(ya[j]);
-                float bb = __uint_as_float(yb[j]) + shfl_dn(yc[j], 1);
-                a = a * sScale[n0 + j] + sShift[n0 + j];
-                bb = bb * sScale[n0 + j] + sShift[n0 + j];
-                if (P.relu) { a = fmaxf(a, 0.f); bb = fmaxf(bb, 0.f); }
-                r0.v[j] = a; r1.v[j] = bb;
-              }
-              if (valid && P.n0 + n0 < P.Cout) {
-                const int go = P.out_g0 + n0 / 8;
-                const size_t off = g8_offset(b, go, zo, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
-                if (P.skip) {
-                  F8 s0 = load8(P.skip + off), s1 = load8(P.skip + off + 8);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) { r0.v[j] += s0.v[j]; r1.v[j] += s1.v[j]; }
-                }
-                __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + off;
-                store8(o, r0);
-                store8(o + 8, r1);
-              }
-            }
-          }
-        } else {
-          int yo, xo;
-          bool valid;
-          if (MODE == MODE_S1) {
-            yo = ty0 + ty; xo = tx0 + tx;
-            valid = tx < G_::TW && yo < P.Hout && xo < P.Wout;
+        for (int u = 0; u < U; ++u) {
+          const int k = u / (MC * CPG), c = (u / CPG) % MC, ng = u % CPG;
+          const int pdh = 2 * half + k, pd = pdh >> 1, ph = pdh & 1;
+          const int yi = ty0 + c * 4 + q, xi = tx0 + lane;
+          offs[u] = g8_offset(b, P.out_g0 + ng, 2 * it + pd, 2 * yi + ph, 2 * xi, P.out_G, P.Dout, P.Hout, P.Wout);
+          if (P.skip && valid[c] && ng < ngroups) {
+            sk[u][0] = __ldg(reinterpret_cast<const uint4*>(P.skip + offs[u]));
+            sk[u][1] = __ldg(reinterpret_cast<const uint4*>(P.skip + offs[u] + 8));
           } else {
-            yo = ty0 + ty; xo = tx0 + (tx >> 1);
-            valid = !(tx & 1) && (tx >> 1) < G_::TW && yo < P.Hout && xo < P.Wout;
+            sk[u][0] = sk[u][1] = make_uint4(0, 0, 0, 0);
           }
-          const uint32_t cbase = tbase + c * N;
+        }
+        mbar_wait(&tmem_full[buf], (NBUF == 2 ? (it >> 1) : it) & 1);
+        tc_fence_after();
+        if (warp == 2 && lane == 0 && it < 12) TRACE(28 + it);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int k = u / (MC * CPG), c = (u / CPG) % MC, ng = u % CPG;
+          if (ng >= ngroups) continue;   // uniform
+          const int pdh = 2 * half + k;
+          const uint32_t cbase = tbase + (pdh * MC + c) * N + ng * 8;
+          uint32_t ya[8], yb[8], yc[8];  // tw = 1 (even x), tw = 2 (odd x, same input), tw = 0 (odd x, input + 1)
+          tmem_ld8(cbase, ya);
+          tmem_ld8(cbase + CP, yb);
+          tmem_ld8(cbase + 2 * CP, yc);
+          tmem_ld_wait();
+          F8 r0, r1;
+          const uint32_t s0[4] = {sk[u][0].x, sk[u][0].y, sk[u][0].z, sk[u][0].w};
+          const uint32_t s1[4] = {sk[u][1].x, sk[u][1].y, sk[u][1].z, sk[u][1].w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float a = __uint_as_float(ya[j]);
+            float bb = __uint_as_float(yb[j]) + shfl_dn(yc[j], 1);
+            a = a * sScale[ng * 8 + j] + sShift[ng * 8 + j];
+            bb = bb * sScale[ng * 8 + j] + sShift[ng * 8 + j];
+            if (P.relu) { a = fmaxf(a, 0.f); bb = fmaxf(bb, 0.f); }
+            const uint32_t w0 = s0[j >> 1], w1 = s1[j >> 1];
+            r0.v[j] = a + __uint_as_float((j & 1) ? (w0 & 0xffff0000u) : (w0 << 16));
+            r1.v[j] = bb + __uint_as_float((j & 1) ? (w1 & 0xffff0000u) : (w1 << 16));
+          }
+          if (valid[c]) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + offs[u];
+            store8(o, r0);
+            store8(o + 8, r1);
+          }
+        }
+      } else {
+        // units: MC == 2: this half's chunk x all groups; MC == 1: chunk 0, groups ng == half (mod 2)
+        constexpr int U = MC >= 2 ? (MC / 2) * CPG : (CPG + 1) / 2;
+        uint4 sk[U];
+        size_t offs[U];
+        bool valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int c = MC >= 2 ? half * (MC / 2) + u / CPG : 0;
+          const int ng = MC >= 2 ? u % CPG : 2 * u + half;
+          const int ty = c * 4 + q, tx = lane;
+          int yo = ty0 + ty, xo;
+          if (MODE == MODE_S1) { xo = tx0 + tx; valid[u] = tx < G_::TW && yo < P.Hout && xo < P.Wout; }
+          else { xo = tx0 + (tx >> 1); valid[u] = !(tx & 1) && (tx >> 1) < G_::TW && yo < P.Hout && xo < P.Wout; }
+          if (P.plain_out) offs[u] = (size_t)(((long long)b * P.Dout + it) * HWo + (long long)yo * P.Wout + xo);
+          else offs[u] = g8_offset(b, P.out_g0 + ng, it, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
+          sk[u] = (P.skip && valid[u] && ng < ngroups) ? __ldg(reinterpret_cast<const uint4*>(P.skip + offs[u])) : make_uint4(0, 0, 0, 0);
+        }
+        mbar_wait(&tmem_full[buf], (NBUF == 2 ? (it >> 1) : it) & 1);
+        tc_fence_after();
+        if (warp == 2 && lane == 0 && it < 12) TRACE(28 + it);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int c = MC >= 2 ? half * (MC / 2) + u / CPG : 0;
+          const int ng = MC >= 2 ? u % CPG : 2 * u + half;
+          if (ng >= ngroups) continue;   // uniform
+          const uint32_t cbase = tbase + c * N + ng * 8;
           if (P.plain_out) {
             uint32_t y0, y1, y2;
             tmem_ld1(cbase, y0);
@@ -386,33 +418,24 @@ __global__ void __launch_bounds__(192) conv3d_tc_kernel(const __grid_constant__ 
             tmem_ld1(cbase + 2 * CP, y2);
             tmem_ld_wait();
             const float v = __uint_as_float(y0) + shfl_dn(y1, 1) + shfl_dn(y2, 2);
-            if (valid) reinterpret_cast<float*>(P.out)[((long long)b * P.Dout + it) * HWo + (long long)yo * P.Wout + xo] = v;
+            if (valid[u]) reinterpret_cast<float*>(P.out)[offs[u]] = v;
           } else {
-#pragma unroll 1
-            for (int n0 = 0; n0 < CP; n0 += 8) {
-              uint32_t y0[8], y1[8], y2[8];
-              tmem_ld8(cbase + n0, y0);
-              tmem_ld8(cbase + CP + n0, y1);
-              tmem_ld8(cbase + 2 * CP + n0, y2);
-              tmem_ld_wait();
-              F8 r;
+            uint32_t y0[8], y1[8], y2[8];
+            tmem_ld8(cbase, y0);
+            tmem_ld8(cbase + CP, y1);
+            tmem_ld8(cbase + 2 * CP, y2);
+            tmem_ld_wait();
+            F8 r;
+            const uint32_t sw[4] = {sk[u].x, sk[u].y, sk[u].z, sk[u].w};
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float a = __uint_as_float(y0[j]) + shfl_dn(y1[j], 1) + shfl_dn(y2[j], 2);
-                a = a * sScale[n0 + j] + sShift[n0 + j];
-                r.v[j] = P.relu ? fmaxf(a, 0.f) : a;
-              }
-              if (valid && P.n0 + n0 < P.Cout) {
-                const int go = P.out_g0 + n0 / 8;
-                const size_t off = g8_offset(b, go, it, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
-                if (P.skip) {
-                  F8 s = load8(P.skip + off);
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) r.v[j] += s.v[j];
-                }
-                store8(reinterpret_cast<__nv_bfloat16*>(P.out) + off, r);
-              }
+            for (int j = 0; j < 8; ++j) {
+              float a = __uint_as_float(y0[j]) + shfl_dn(y1[j], 1) + shfl_dn(y2[j], 2);
+              a = a * sScale[ng * 8 + j] + sShift[ng * 8 + j];
+              if (P.relu) a = fmaxf(a, 0.f);
+              const uint32_t w = sw[j >> 1];
+              r.v[j] = a + __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
             }
+            if (valid[u]) store8(reinterpret_cast<__nv_bfloat16*>(P.out) + offs[u], r);
           }
         }
       }
@@ -652,7 +675,7 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
     cudaMalloc(&dbuf, n * 8);
     cudaMemset(dbuf, 0, n * 8);
     P.trace = dbuf;
-    kern<<<grid, 192, smem, st>>>(m0, m1, P);
+    kern<<<grid, 320, smem, st>>>(m0, m1, P);
     cudaStreamSynchronize(st);
     std::vector<unsigned long long> h(n);
     cudaMemcpy(h.data(), dbuf, n * 8, cudaMemcpyDeviceToHost);
@@ -673,7 +696,7 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
     }
     return DAMVS_OK;
   }
-  kern<<<grid, 192, smem, st>>>(m0, m1, P);
+  kern<<<grid, 320, smem, st>>>(m0, m1, P);
   DAMVS_LAUNCH_OK("conv3d_tc kernel");
   return DAMVS_OK;
 }
