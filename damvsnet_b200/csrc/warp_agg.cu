@@ -93,13 +93,53 @@ __device__ __forceinline__ float4 sample4(const float* __restrict__ img, int H, 
   return acc;
 }
 
+// One bilinear footprint in "always addressable" form: `off` is the element offset of a 2x2 tap block
+// that lies inside the image, and the four weights are ATen's (nw, ne, sw, se) products with the weight
+// of every out-of-range tap set to zero and re-assigned to the in-range tap the clamped block maps it to.
+struct Footprint {
+  float w00, w01, w10, w11;
+  int off;
+};
+
+__device__ __forceinline__ Footprint make_footprint(float ix, float iy, int H, int W, int C) {
+  Footprint f;
+  f.w00 = f.w01 = f.w10 = f.w11 = 0.f;
+  f.off = 0;
+  // NaN / far-out-of-range coordinates sample nothing (ATen returns NaN for NaN coordinates; the
+  // synthetic inputs keep z != 0)
+  if (!(ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H)) return f;
+  const float fx0 = floorf(ix), fy0 = floorf(iy);
+  const int x0 = (int)fx0, y0 = (int)fy0;
+  float wl = (fx0 + 1.f) - ix, wr = ix - fx0;   // weights of columns x0, x0+1
+  float wt = (fy0 + 1.f) - iy, wb = iy - fy0;   // weights of rows y0, y0+1
+  int xc = x0, yc = y0;
+  if (x0 < 0) { xc = 0; wl = wr; wr = 0.f; }                 // only column 0 (the old right tap) is in range
+  else if (x0 > W - 2) { xc = W - 2; wr = wl; wl = 0.f; }    // only column W-1 (the old left tap) is in range
+  if (y0 < 0) { yc = 0; wt = wb; wb = 0.f; }
+  else if (y0 > H - 2) { yc = H - 2; wb = wt; wt = 0.f; }
+  f.w00 = wl * wt; f.w01 = wr * wt; f.w10 = wl * wb; f.w11 = wr * wb;
+  f.off = (yc * W + xc) * C;
+  return f;
+}
+
+// Mapping: a thread owns (pixel, 4 consecutive channels); the C/4 lanes of a pixel are adjacent in the warp.
+// Depth hypotheses are processed in chunks of DCH; inside a chunk the loop order is (source view, depth):
+//   * the C/4 lanes of a pixel split the DCH projections of (view, chunk) between them and publish the
+//     footprints through shared memory, so the ~60-instruction projection is computed once per
+//     (pixel, view, depth) instead of once per lane;
+//   * walking depth innermost, consecutive hypotheses of the cascade's later stages land in the same 2x2
+//     tap block most of the time (sub-pixel steps along the epipolar line): the four 16-byte taps stay in
+//     registers and are only re-fetched when the block changes.
 template <int C, int MODE, typename OutT>
 __global__ void __launch_bounds__(256) warp_agg_kernel(const WarpAggParams P) {
   constexpr int LPP = C / 4;     // lanes per pixel
   constexpr int PPW = 32 / LPP;  // pixels per warp (along x)
   constexpr int TW = 2 * PPW, TH = 4;
+  constexpr int DCH = 8;         // depth chunk
   __shared__ float s_rt[kMaxSrc * 12];
   __shared__ float s_wnet[C + 5];
+  __shared__ float4 s_fw[8][PPW][DCH + 1];
+  __shared__ int s_fo[8][PPW][DCH + 1];
 
   const int b = blockIdx.z;
   const int H = P.H, W = P.W, D = P.D, n_src = P.n_src;
@@ -113,7 +153,8 @@ __global__ void __launch_bounds__(256) warp_agg_kernel(const WarpAggParams P) {
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = lane % LPP;  // channel quad
-  const int px = blockIdx.x * TW + (warp & 1) * PPW + lane / LPP;
+  const int pw = lane / LPP; // pixel within the warp
+  const int px = blockIdx.x * TW + (warp & 1) * PPW + pw;
   const int py = blockIdx.y * TH + (warp >> 1);
   const bool live = px < W && py < H;
   const int x = live ? px : 0, y = live ? py : 0;
@@ -138,46 +179,95 @@ __global__ void __launch_bounds__(256) warp_agg_kernel(const WarpAggParams P) {
   const long long out_stride = HW * 8;
   const float inv_n = 1.f / (float)(n_src + 1), inv_nsrc = 1.f / (float)n_src;
 
-  for (int d = 0; d < D; ++d) {
-    const float dep = __ldg(hyp + d * hyp_stride);
-    float a0, a1, a2, a3, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
-    if (MODE == DAMVS_AGG_VARIANCE) {
-      a0 = rf.x; a1 = rf.y; a2 = rf.z; a3 = rf.w;
-      q0 = rf.x * rf.x; q1 = rf.y * rf.y; q2 = rf.z * rf.z; q3 = rf.w * rf.w;
-    } else {
-      a0 = a1 = a2 = a3 = 0.f;
+  for (int d0 = 0; d0 < D; d0 += DCH) {
+    float acc[DCH][4], sq[DCH][4];
+#pragma unroll
+    for (int j = 0; j < DCH; ++j) {
+      if (MODE == DAMVS_AGG_VARIANCE) {
+        acc[j][0] = rf.x; acc[j][1] = rf.y; acc[j][2] = rf.z; acc[j][3] = rf.w;
+        sq[j][0] = rf.x * rf.x; sq[j][1] = rf.y * rf.y; sq[j][2] = rf.z * rf.z; sq[j][3] = rf.w * rf.w;
+      } else {
+        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+      }
+    }
+    // hypotheses this lane projects: j = q, q + LPP, ...
+    float dep[(DCH + LPP - 1) / LPP];
+#pragma unroll
+    for (int k = 0; k < (DCH + LPP - 1) / LPP; ++k) {
+      const int d = d0 + q + k * LPP;
+      dep[k] = (q + k * LPP < DCH && d < D) ? __ldg(hyp + d * hyp_stride) : 1.f;
     }
     for (int v = 0; v < n_src; ++v) {
       const float* rt = s_rt + v * 12;
       // rot @ [x, y, 1]  (models/module.py:317)
-      float rx = fmaf(rt[0], fx, fmaf(rt[1], fy, rt[2]));
-      float ry = fmaf(rt[3], fx, fmaf(rt[4], fy, rt[5]));
-      float rz = fmaf(rt[6], fx, fmaf(rt[7], fy, rt[8]));
-      float ix, iy;
-      project(rt, rx, ry, rz, dep, half_w, half_h, fw, fh, ix, iy);
-      float4 wv = sample4(P.src[v] + (long long)b * img_stride, H, W, C, c0, ix, iy);
-      if (MODE == DAMVS_AGG_VARIANCE) {
-        a0 += wv.x; a1 += wv.y; a2 += wv.z; a3 += wv.w;
-        q0 += wv.x * wv.x; q1 += wv.y * wv.y; q2 += wv.z * wv.z; q3 += wv.w * wv.w;
-      } else {
-        float e0 = rf.x - wv.x, e1 = rf.y - wv.y, e2 = rf.z - wv.z, e3 = rf.w - wv.w;
-        e0 *= e0; e1 *= e1; e2 *= e2; e3 *= e3;                       // cas_mvsnet.py:66
-        float s = w1[0] * e0 + w1[1] * e1 + w1[2] * e2 + w1[3] * e3;  // 1x1x1 conv C->1
+      const float rx = fmaf(rt[0], fx, fmaf(rt[1], fy, rt[2]));
+      const float ry = fmaf(rt[3], fx, fmaf(rt[4], fy, rt[5]));
+      const float rz = fmaf(rt[6], fx, fmaf(rt[7], fy, rt[8]));
 #pragma unroll
-        for (int o = LPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        float a = fmaxf(s * s1 + b1, 0.f);                            // BN + ReLU
-        float wt = fmaxf((a * w2) * s2 + b2, 0.f) + 1.f;              // conv 1->1, BN, ReLU; (weight + 1)
-        a0 += wt * e0; a1 += wt * e1; a2 += wt * e2; a3 += wt * e3;   // cas_mvsnet.py:73-76
+      for (int k = 0; k < (DCH + LPP - 1) / LPP; ++k) {
+        const int j = q + k * LPP;
+        if (j < DCH) {
+          float ix, iy;
+          project(rt, rx, ry, rz, dep[k], half_w, half_h, fw, fh, ix, iy);
+          const Footprint f = make_footprint(ix, iy, H, W, C);
+          s_fw[warp][pw][j] = make_float4(f.w00, f.w01, f.w10, f.w11);
+          s_fo[warp][pw][j] = f.off;
+        }
+      }
+      __syncwarp();
+      const float* img = P.src[v] + (long long)b * img_stride + c0;
+      int cur = -1;
+      float4 t00 = make_float4(0.f, 0.f, 0.f, 0.f), t01 = t00, t10 = t00, t11 = t00;
+#pragma unroll
+      for (int j = 0; j < DCH; ++j) {
+        if (d0 + j < D) {  // uniform
+          const float4 fwt = s_fw[warp][pw][j];
+          const int off = s_fo[warp][pw][j];
+          if (off != cur) {
+            const float* p = img + off;
+            t00 = __ldg(reinterpret_cast<const float4*>(p));
+            t01 = __ldg(reinterpret_cast<const float4*>(p + C));
+            t10 = __ldg(reinterpret_cast<const float4*>(p + (long long)W * C));
+            t11 = __ldg(reinterpret_cast<const float4*>(p + (long long)W * C + C));
+            cur = off;
+          }
+          // ATen grid_sampler_2d accumulation order: nw, ne, sw, se
+          float4 wv;
+          wv.x = t00.x * fwt.x; wv.y = t00.y * fwt.x; wv.z = t00.z * fwt.x; wv.w = t00.w * fwt.x;
+          wv.x += t01.x * fwt.y; wv.y += t01.y * fwt.y; wv.z += t01.z * fwt.y; wv.w += t01.w * fwt.y;
+          wv.x += t10.x * fwt.z; wv.y += t10.y * fwt.z; wv.z += t10.z * fwt.z; wv.w += t10.w * fwt.z;
+          wv.x += t11.x * fwt.w; wv.y += t11.y * fwt.w; wv.z += t11.z * fwt.w; wv.w += t11.w * fwt.w;
+          if (MODE == DAMVS_AGG_VARIANCE) {
+            acc[j][0] += wv.x; acc[j][1] += wv.y; acc[j][2] += wv.z; acc[j][3] += wv.w;
+            sq[j][0] += wv.x * wv.x; sq[j][1] += wv.y * wv.y; sq[j][2] += wv.z * wv.z; sq[j][3] += wv.w * wv.w;
+          } else {
+            float e0 = rf.x - wv.x, e1 = rf.y - wv.y, e2 = rf.z - wv.z, e3 = rf.w - wv.w;
+            e0 *= e0; e1 *= e1; e2 *= e2; e3 *= e3;                       // cas_mvsnet.py:66
+            float s = w1[0] * e0 + w1[1] * e1 + w1[2] * e2 + w1[3] * e3;  // 1x1x1 conv C->1
+#pragma unroll
+            for (int o = LPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float a = fmaxf(s * s1 + b1, 0.f);                      // BN + ReLU
+            const float wt = fmaxf((a * w2) * s2 + b2, 0.f) + 1.f;        // conv 1->1, BN, ReLU; (weight + 1)
+            acc[j][0] += wt * e0; acc[j][1] += wt * e1; acc[j][2] += wt * e2; acc[j][3] += wt * e3;  // cas_mvsnet.py:73-76
+          }
+        }
+      }
+      __syncwarp();  // footprints of this view are consumed before the next view overwrites them
+    }
+#pragma unroll
+    for (int j = 0; j < DCH; ++j) {
+      if (d0 + j < D) {
+        float a0, a1, a2, a3;
+        if (MODE == DAMVS_AGG_VARIANCE) {
+          const float m0 = acc[j][0] * inv_n, m1 = acc[j][1] * inv_n, m2 = acc[j][2] * inv_n, m3 = acc[j][3] * inv_n;
+          a0 = sq[j][0] * inv_n - m0 * m0; a1 = sq[j][1] * inv_n - m1 * m1;   // cas_mvsnet.py:85
+          a2 = sq[j][2] * inv_n - m2 * m2; a3 = sq[j][3] * inv_n - m3 * m3;
+        } else {
+          a0 = acc[j][0] * inv_nsrc; a1 = acc[j][1] * inv_nsrc; a2 = acc[j][2] * inv_nsrc; a3 = acc[j][3] * inv_nsrc;  // cas_mvsnet.py:87
+        }
+        if (live) store4(out + (long long)(d0 + j) * out_stride, a0, a1, a2, a3);
       }
     }
-    if (MODE == DAMVS_AGG_VARIANCE) {
-      float m0 = a0 * inv_n, m1 = a1 * inv_n, m2 = a2 * inv_n, m3 = a3 * inv_n;
-      a0 = q0 * inv_n - m0 * m0; a1 = q1 * inv_n - m1 * m1;            // cas_mvsnet.py:85
-      a2 = q2 * inv_n - m2 * m2; a3 = q3 * inv_n - m3 * m3;
-    } else {
-      a0 *= inv_nsrc; a1 *= inv_nsrc; a2 *= inv_nsrc; a3 *= inv_nsrc;  // cas_mvsnet.py:87
-    }
-    if (live) store4(out + d * out_stride, a0, a1, a2, a3);
   }
 }
 
@@ -234,7 +324,7 @@ extern "C" int damvs_warp_agg_fwd(const float* ref_nhwc, const float* const* src
                                   void* stream) {
   DAMVS_REQUIRE(ref_nhwc && src_nhwc && rot_trans && depth_hyp && out_vol, "warp_agg: null pointer");
   DAMVS_REQUIRE(n_src >= 1 && n_src <= kMaxSrc, "warp_agg: n_src=%d outside [1,%d]", n_src, kMaxSrc);
-  DAMVS_REQUIRE(B > 0 && D > 0 && H > 0 && W > 0, "warp_agg: bad shape B=%d D=%d H=%d W=%d", B, D, H, W);
+  DAMVS_REQUIRE(B > 0 && D > 0 && H > 1 && W > 1, "warp_agg: bad shape B=%d D=%d H=%d W=%d (H, W >= 2)", B, D, H, W);
   DAMVS_REQUIRE(B <= 65535, "warp_agg: B too large");
   DAMVS_REQUIRE(mode == DAMVS_AGG_VARIANCE || mode == DAMVS_AGG_ADAPTIVE, "warp_agg: bad mode %d", mode);
   DAMVS_REQUIRE(mode == DAMVS_AGG_VARIANCE || wnet != nullptr, "warp_agg: adaptive mode needs wnet");
