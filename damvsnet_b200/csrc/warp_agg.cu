@@ -43,15 +43,16 @@ struct WarpAggParams {
 
 // source coordinates of reference pixel (x,y) at depth d, exactly in the
 // reference's operation order (mul, add, div kept un-contracted)
-__device__ __forceinline__ void project(const float* rt, float rx, float ry, float rz, float d, float half_w,
-                                        float half_h, float fw, float fh, float& ix, float& iy) {
+__device__ __forceinline__ void project(const float* rt, float rx, float ry, float rz, float d, float inv_half_w,
+                                        float inv_half_h, float fw, float fh, float& ix, float& iy) {
   float px = __fadd_rn(__fmul_rn(rx, d), rt[9]);
   float py = __fadd_rn(__fmul_rn(ry, d), rt[10]);
   float pz = __fadd_rn(__fmul_rn(rz, d), rt[11]);
   float u = __fdiv_rn(px, pz);
   float v = __fdiv_rn(py, pz);
-  float gx = __fadd_rn(__fdiv_rn(u, half_w), -1.f);  // models/module.py:323
-  float gy = __fadd_rn(__fdiv_rn(v, half_h), -1.f);  // models/module.py:324
+  // tensor / python-scalar: ATen's CUDA div kernel multiplies by the fp32 reciprocal of a CPU scalar divisor
+  float gx = __fadd_rn(__fmul_rn(u, inv_half_w), -1.f);  // models/module.py:323
+  float gy = __fadd_rn(__fmul_rn(v, inv_half_h), -1.f);  // models/module.py:324
   // ATen grid_sampler_unnormalize, align_corners=False
   ix = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gx, 1.f), fw), -1.f), 0.5f);
   iy = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(gy, 1.f), fh), -1.f), 0.5f);
@@ -122,24 +123,43 @@ __device__ __forceinline__ Footprint make_footprint(float ix, float iy, int H, i
   return f;
 }
 
-// Mapping: a thread owns (pixel, 4 consecutive channels); the C/4 lanes of a pixel are adjacent in the warp.
-// Depth hypotheses are processed in chunks of DCH; inside a chunk the loop order is (source view, depth):
-//   * the C/4 lanes of a pixel split the DCH projections of (view, chunk) between them and publish the
-//     footprints through shared memory, so the ~60-instruction projection is computed once per
-//     (pixel, view, depth) instead of once per lane;
-//   * walking depth innermost, consecutive hypotheses of the cascade's later stages land in the same 2x2
-//     tap block most of the time (sub-pixel steps along the epipolar line): the four 16-byte taps stay in
-//     registers and are only re-fetched when the block changes.
-template <int C, int MODE, typename OutT>
-__global__ void __launch_bounds__(256) warp_agg_kernel(const WarpAggParams P) {
-  constexpr int LPP = C / 4;     // lanes per pixel
+// packed fp32x2 arithmetic (sm_100 FFMA2/FADD2/FMUL2): halves the issue slots of the per-channel math
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
+
+struct Tap8 {
+  float2 v[4];
+};
+__device__ __forceinline__ Tap8 load_tap8(const float* p) {
+  Tap8 t;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  t.v[0] = make_float2(a.x, a.y); t.v[1] = make_float2(a.z, a.w);
+  t.v[2] = make_float2(b.x, b.y); t.v[3] = make_float2(b.z, b.w);
+  return t;
+}
+
+// Mapping: a thread owns (pixel, 8 consecutive channels = one G8 group); the C/8 lanes of a pixel are adjacent
+// in the warp (C = 8: one thread per pixel, no cross-lane traffic at all).  Depth hypotheses are processed in
+// chunks of DCH; inside a chunk the loop order is (source view, depth):
+//   * the lanes of a pixel split the DCH projections of (view, chunk) between them and publish the footprints
+//     through shared memory, so the ~60-instruction projection is computed once per (pixel, view, depth);
+//   * walking depth innermost, consecutive hypotheses of the cascade's later stages land in the same 2x2 tap
+//     block most of the time (sub-pixel steps along the epipolar line): the taps stay in registers and are
+//     only re-fetched when the block changes;
+//   * the per-channel math runs on packed fp32x2 instructions.
+template <int C, int MODE, typename OutT, int DCH>
+__global__ void __launch_bounds__(128) warp_agg_kernel(const WarpAggParams P) {
+  constexpr int LPP = C / 8;     // lanes per pixel
   constexpr int PPW = 32 / LPP;  // pixels per warp (along x)
-  constexpr int TW = 2 * PPW, TH = 4;
-  constexpr int DCH = 8;         // depth chunk
+  constexpr int TW = PPW, TH = 4;  // 4 warps, one pixel row each
+  constexpr int NPJ = (DCH + LPP - 1) / LPP;
   __shared__ float s_rt[kMaxSrc * 12];
   __shared__ float s_wnet[C + 5];
-  __shared__ float4 s_fw[8][PPW][DCH + 1];
-  __shared__ int s_fo[8][PPW][DCH + 1];
+  __shared__ float4 s_fw[LPP > 1 ? 4 : 1][LPP > 1 ? PPW : 1][DCH + 1];
+  __shared__ int s_fo[LPP > 1 ? 4 : 1][LPP > 1 ? PPW : 1][DCH + 1];
 
   const int b = blockIdx.z;
   const int H = P.H, W = P.W, D = P.D, n_src = P.n_src;
@@ -152,50 +172,52 @@ __global__ void __launch_bounds__(256) warp_agg_kernel(const WarpAggParams P) {
   __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = lane % LPP;  // channel quad
+  const int q = lane % LPP;  // channel group
   const int pw = lane / LPP; // pixel within the warp
-  const int px = blockIdx.x * TW + (warp & 1) * PPW + pw;
-  const int py = blockIdx.y * TH + (warp >> 1);
+  const int px = blockIdx.x * TW + pw;
+  const int py = blockIdx.y * TH + warp;
   const bool live = px < W && py < H;
   const int x = live ? px : 0, y = live ? py : 0;
-  const int c0 = q * 4;
+  const int c0 = q * 8;
   const long long HW = (long long)H * W;
   const long long img_stride = HW * C;
 
-  const float4 rf = __ldg(reinterpret_cast<const float4*>(P.ref + (long long)b * img_stride + ((long long)y * W + x) * C + c0));
+  const Tap8 rf = load_tap8(P.ref + (long long)b * img_stride + ((long long)y * W + x) * C + c0);
   const float fx = (float)x, fy = (float)y;
-  const float half_w = (float)((W - 1) / 2.0), half_h = (float)((H - 1) / 2.0);
+  const float inv_half_w = 1.f / (float)((W - 1) / 2.0), inv_half_h = 1.f / (float)((H - 1) / 2.0);
   const float fw = (float)W, fh = (float)H;
-  float w1[4] = {0.f, 0.f, 0.f, 0.f};
+  float2 w1[4];
   float s1 = 0.f, b1 = 0.f, w2 = 0.f, s2 = 0.f, b2 = 0.f;
   if (MODE == DAMVS_AGG_ADAPTIVE) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w1[j] = s_wnet[c0 + j];
+    for (int j = 0; j < 4; ++j) w1[j] = make_float2(s_wnet[c0 + 2 * j], s_wnet[c0 + 2 * j + 1]);
     s1 = s_wnet[C]; b1 = s_wnet[C + 1]; w2 = s_wnet[C + 2]; s2 = s_wnet[C + 3]; b2 = s_wnet[C + 4];
   }
   const float* hyp = P.per_pixel ? P.hyp + (long long)b * D * HW + (long long)y * W + x : P.hyp + (long long)b * D;
   const long long hyp_stride = P.per_pixel ? HW : 1;
-  OutT* out = reinterpret_cast<OutT*>(P.out) + g8_offset(b, q >> 1, 0, y, x, C / 8, D, H, W) + (q & 1) * 4;
+  OutT* out = reinterpret_cast<OutT*>(P.out) + g8_offset(b, q, 0, y, x, C / 8, D, H, W);
   const long long out_stride = HW * 8;
   const float inv_n = 1.f / (float)(n_src + 1), inv_nsrc = 1.f / (float)n_src;
 
   for (int d0 = 0; d0 < D; d0 += DCH) {
-    float acc[DCH][4], sq[DCH][4];
+    float2 acc[DCH][4], sq[MODE == DAMVS_AGG_VARIANCE ? DCH : 1][4];
 #pragma unroll
-    for (int j = 0; j < DCH; ++j) {
-      if (MODE == DAMVS_AGG_VARIANCE) {
-        acc[j][0] = rf.x; acc[j][1] = rf.y; acc[j][2] = rf.z; acc[j][3] = rf.w;
-        sq[j][0] = rf.x * rf.x; sq[j][1] = rf.y * rf.y; sq[j][2] = rf.z * rf.z; sq[j][3] = rf.w * rf.w;
-      } else {
-        acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    for (int j = 0; j < DCH; ++j)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (MODE == DAMVS_AGG_VARIANCE) {
+          acc[j][k] = rf.v[k];
+          sq[j][k] = mul2(rf.v[k], rf.v[k]);
+        } else {
+          acc[j][k] = make_float2(0.f, 0.f);
+        }
       }
-    }
     // hypotheses this lane projects: j = q, q + LPP, ...
-    float dep[(DCH + LPP - 1) / LPP];
+    float dep[NPJ];
 #pragma unroll
-    for (int k = 0; k < (DCH + LPP - 1) / LPP; ++k) {
-      const int d = d0 + q + k * LPP;
-      dep[k] = (q + k * LPP < DCH && d < D) ? __ldg(hyp + d * hyp_stride) : 1.f;
+    for (int k = 0; k < NPJ; ++k) {
+      const int j = q + k * LPP, d = d0 + j;
+      dep[k] = (j < DCH && d < D) ? __ldg(hyp + d * hyp_stride) : 1.f;
     }
     for (int v = 0; v < n_src; ++v) {
       const float* rt = s_rt + v * 12;
@@ -203,69 +225,96 @@ __global__ void __launch_bounds__(256) warp_agg_kernel(const WarpAggParams P) {
       const float rx = fmaf(rt[0], fx, fmaf(rt[1], fy, rt[2]));
       const float ry = fmaf(rt[3], fx, fmaf(rt[4], fy, rt[5]));
       const float rz = fmaf(rt[6], fx, fmaf(rt[7], fy, rt[8]));
+      Footprint fp[LPP > 1 ? 1 : DCH];
 #pragma unroll
-      for (int k = 0; k < (DCH + LPP - 1) / LPP; ++k) {
+      for (int k = 0; k < NPJ; ++k) {
         const int j = q + k * LPP;
         if (j < DCH) {
           float ix, iy;
-          project(rt, rx, ry, rz, dep[k], half_w, half_h, fw, fh, ix, iy);
+          project(rt, rx, ry, rz, dep[k], inv_half_w, inv_half_h, fw, fh, ix, iy);
           const Footprint f = make_footprint(ix, iy, H, W, C);
-          s_fw[warp][pw][j] = make_float4(f.w00, f.w01, f.w10, f.w11);
-          s_fo[warp][pw][j] = f.off;
+          if (LPP > 1) {
+            s_fw[warp][pw][j] = make_float4(f.w00, f.w01, f.w10, f.w11);
+            s_fo[warp][pw][j] = f.off;
+          } else {
+            fp[k] = f;
+          }
         }
       }
-      __syncwarp();
+      if (LPP > 1) __syncwarp();
       const float* img = P.src[v] + (long long)b * img_stride + c0;
       int cur = -1;
-      float4 t00 = make_float4(0.f, 0.f, 0.f, 0.f), t01 = t00, t10 = t00, t11 = t00;
+      Tap8 t00, t01, t10, t11;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) t00.v[k] = t01.v[k] = t10.v[k] = t11.v[k] = make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < DCH; ++j) {
         if (d0 + j < D) {  // uniform
-          const float4 fwt = s_fw[warp][pw][j];
-          const int off = s_fo[warp][pw][j];
+          float4 fwt;
+          int off;
+          if (LPP > 1) {
+            fwt = s_fw[warp][pw][j];
+            off = s_fo[warp][pw][j];
+          } else {
+            fwt = make_float4(fp[j].w00, fp[j].w01, fp[j].w10, fp[j].w11);
+            off = fp[j].off;
+          }
           if (off != cur) {
             const float* p = img + off;
-            t00 = __ldg(reinterpret_cast<const float4*>(p));
-            t01 = __ldg(reinterpret_cast<const float4*>(p + C));
-            t10 = __ldg(reinterpret_cast<const float4*>(p + (long long)W * C));
-            t11 = __ldg(reinterpret_cast<const float4*>(p + (long long)W * C + C));
+            t00 = load_tap8(p);
+            t01 = load_tap8(p + C);
+            t10 = load_tap8(p + (long long)W * C);
+            t11 = load_tap8(p + (long long)W * C + C);
             cur = off;
           }
-          // ATen grid_sampler_2d accumulation order: nw, ne, sw, se
-          float4 wv;
-          wv.x = t00.x * fwt.x; wv.y = t00.y * fwt.x; wv.z = t00.z * fwt.x; wv.w = t00.w * fwt.x;
-          wv.x += t01.x * fwt.y; wv.y += t01.y * fwt.y; wv.z += t01.z * fwt.y; wv.w += t01.w * fwt.y;
-          wv.x += t10.x * fwt.z; wv.y += t10.y * fwt.z; wv.z += t10.z * fwt.z; wv.w += t10.w * fwt.z;
-          wv.x += t11.x * fwt.w; wv.y += t11.y * fwt.w; wv.z += t11.z * fwt.w; wv.w += t11.w * fwt.w;
+          const float2 a00 = splat(fwt.x), a01 = splat(fwt.y), a10 = splat(fwt.z), a11 = splat(fwt.w);
+          float2 wv[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // ATen grid_sampler_2d accumulation order: nw, ne, sw, se
+            wv[k] = fma2(t11.v[k], a11, fma2(t10.v[k], a10, fma2(t01.v[k], a01, mul2(t00.v[k], a00))));
           if (MODE == DAMVS_AGG_VARIANCE) {
-            acc[j][0] += wv.x; acc[j][1] += wv.y; acc[j][2] += wv.z; acc[j][3] += wv.w;
-            sq[j][0] += wv.x * wv.x; sq[j][1] += wv.y * wv.y; sq[j][2] += wv.z * wv.z; sq[j][3] += wv.w * wv.w;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              acc[j][k] = add2(acc[j][k], wv[k]);
+              sq[j][k] = fma2(wv[k], wv[k], sq[j][k]);
+            }
           } else {
-            float e0 = rf.x - wv.x, e1 = rf.y - wv.y, e2 = rf.z - wv.z, e3 = rf.w - wv.w;
-            e0 *= e0; e1 *= e1; e2 *= e2; e3 *= e3;                       // cas_mvsnet.py:66
-            float s = w1[0] * e0 + w1[1] * e1 + w1[2] * e2 + w1[3] * e3;  // 1x1x1 conv C->1
+            float2 e[4], sv = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 df = add2(rf.v[k], make_float2(-wv[k].x, -wv[k].y));
+              e[k] = mul2(df, df);                 // cas_mvsnet.py:66
+              sv = fma2(w1[k], e[k], sv);          // 1x1x1 conv C->1
+            }
+            float s = sv.x + sv.y;
 #pragma unroll
             for (int o = LPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
             const float a = fmaxf(s * s1 + b1, 0.f);                      // BN + ReLU
-            const float wt = fmaxf((a * w2) * s2 + b2, 0.f) + 1.f;        // conv 1->1, BN, ReLU; (weight + 1)
-            acc[j][0] += wt * e0; acc[j][1] += wt * e1; acc[j][2] += wt * e2; acc[j][3] += wt * e3;  // cas_mvsnet.py:73-76
+            const float2 wt = splat(fmaxf((a * w2) * s2 + b2, 0.f) + 1.f);  // conv 1->1, BN, ReLU; (weight + 1)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[j][k] = fma2(wt, e[k], acc[j][k]);   // cas_mvsnet.py:73-76
           }
         }
       }
-      __syncwarp();  // footprints of this view are consumed before the next view overwrites them
+      if (LPP > 1) __syncwarp();  // footprints of this view are consumed before the next view overwrites them
     }
 #pragma unroll
     for (int j = 0; j < DCH; ++j) {
       if (d0 + j < D) {
-        float a0, a1, a2, a3;
-        if (MODE == DAMVS_AGG_VARIANCE) {
-          const float m0 = acc[j][0] * inv_n, m1 = acc[j][1] * inv_n, m2 = acc[j][2] * inv_n, m3 = acc[j][3] * inv_n;
-          a0 = sq[j][0] * inv_n - m0 * m0; a1 = sq[j][1] * inv_n - m1 * m1;   // cas_mvsnet.py:85
-          a2 = sq[j][2] * inv_n - m2 * m2; a3 = sq[j][3] * inv_n - m3 * m3;
-        } else {
-          a0 = acc[j][0] * inv_nsrc; a1 = acc[j][1] * inv_nsrc; a2 = acc[j][2] * inv_nsrc; a3 = acc[j][3] * inv_nsrc;  // cas_mvsnet.py:87
+        F8 r;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float2 a;
+          if (MODE == DAMVS_AGG_VARIANCE) {
+            const float2 m = mul2(acc[j][k], splat(inv_n));
+            const float2 qn = mul2(sq[j][k], splat(inv_n));
+            a = make_float2(qn.x - m.x * m.x, qn.y - m.y * m.y);   // cas_mvsnet.py:85
+          } else {
+            a = mul2(acc[j][k], splat(inv_nsrc));                  // cas_mvsnet.py:87
+          }
+          r.v[2 * k] = a.x; r.v[2 * k + 1] = a.y;
         }
-        if (live) store4(out + (long long)(d0 + j) * out_stride, a0, a1, a2, a3);
+        if (live) store8(out + (long long)(d0 + j) * out_stride, r);
       }
     }
   }
@@ -290,7 +339,7 @@ __global__ void __launch_bounds__(256) homo_warp_kernel(const float* __restrict_
   float rz = fmaf(rt[6], fx, fmaf(rt[7], fy, rt[8]));
   float dep = per_pixel ? __ldg(hyp + ((long long)b * D + d) * HW + pix) : __ldg(hyp + b * D + d);
   float ix, iy;
-  project(rt, rx, ry, rz, dep, (float)((W - 1) / 2.0), (float)((H - 1) / 2.0), (float)W, (float)H, ix, iy);
+  project(rt, rx, ry, rz, dep, 1.f / (float)((W - 1) / 2.0), 1.f / (float)((H - 1) / 2.0), (float)W, (float)H, ix, iy);
   const float* img = src + (long long)b * HW * C;
   float* o = out + (((long long)b * C) * D + d) * HW + pix;
   for (int c0 = 0; c0 < C; c0 += 4) {
@@ -304,12 +353,12 @@ __global__ void __launch_bounds__(256) homo_warp_kernel(const float* __restrict_
 
 template <int C, int MODE>
 static int launch_warp_agg(const WarpAggParams& P, int out_dtype, cudaStream_t st) {
-  constexpr int TW = 2 * (32 / (C / 4)), TH = 4;
+  constexpr int TW = 32 / (C / 8), TH = 4, DCH = 4;
   dim3 grid((P.W + TW - 1) / TW, (P.H + TH - 1) / TH, P.B);
   if (out_dtype == DAMVS_F32)
-    warp_agg_kernel<C, MODE, float><<<grid, 256, 0, st>>>(P);
+    warp_agg_kernel<C, MODE, float, DCH><<<grid, 128, 0, st>>>(P);
   else
-    warp_agg_kernel<C, MODE, __nv_bfloat16><<<grid, 256, 0, st>>>(P);
+    warp_agg_kernel<C, MODE, __nv_bfloat16, DCH><<<grid, 128, 0, st>>>(P);
   DAMVS_LAUNCH_OK("warp_agg kernel");
   return DAMVS_OK;
 }
