@@ -5,80 +5,84 @@
 // store of the probability volume and three [B,H,W] maps.  HBM-bound streaming:
 // algorithmic bytes per pixel = 2*D*4 read + D*4 + 12 written.
 //
-// Mapping: one thread per pixel, the whole D column in registers (D <= 64 for
-// the register path); lanes run along W so every load/store of plane k is a
-// coalesced 128-byte line per warp and a thread has D independent loads in
-// flight.  A column is strided by H*W in memory, so there is nothing to stage
-// in shared memory and nothing to reduce across lanes.
+// Mapping: one thread per pixel; lanes run along W so every load/store of plane
+// k is a coalesced 128-byte line per warp.  A pixel's column is strided by H*W
+// in memory; the main kernel stages a D x 128-pixel tile in shared memory with
+// cp.async, a streaming kernel covers any D / alignment.
 #include "common.cuh"
 
 namespace damvs {
 
-template <int MAXD>
-__global__ void __launch_bounds__(256) head_reg_kernel(const float* __restrict__ logits,
-                                                       const float* __restrict__ hyp, float* __restrict__ prob,
-                                                       float* __restrict__ depth, float* __restrict__ conf,
-                                                       float* __restrict__ var, int D, long long HW,
-                                                       long long total, int per_pixel) {
-  long long pix = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= total) return;
-  long long b = pix / HW;
-  long long p = pix - b * HW;
-  const float* lg = logits + b * D * HW + p;
-  float e[MAXD];
+// Staged variant (D <= 64, H*W % 4 == 0): a CTA owns 128 consecutive pixels; the D x 128 logits and
+// hypotheses tiles are pulled into shared memory with 16-byte cp.async (no registers held while the loads
+// are in flight, so many CTAs per SM keep HBM busy), then every thread walks its own column in shared
+// memory (bank = pixel, conflict free) for max, sum, probabilities, regression, confidence and variance.
+constexpr int kHeadPix = 128;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+
+__global__ void __launch_bounds__(kHeadPix) head_staged_kernel(const float* __restrict__ logits,
+                                                               const float* __restrict__ hyp, float* __restrict__ prob,
+                                                               float* __restrict__ depth, float* __restrict__ conf,
+                                                               float* __restrict__ var, int D, long long HW,
+                                                               int per_pixel) {
+  extern __shared__ __align__(16) float sm[];  // [D][128] logits, then [D][128] hypotheses
+  float* sl = sm;
+  float* sh = sm + D * kHeadPix;
+  const int b = blockIdx.y;
+  const long long p0 = (long long)blockIdx.x * kHeadPix;
+  const int np = (int)min((long long)kHeadPix, HW - p0);  // multiple of 4
+  const int t = threadIdx.x;
+  const float* lg = logits + (long long)b * D * HW + p0;
+  const float* hg = hyp + (long long)b * D * HW + p0;
+  // 32 threads cover one plane's 128 pixels with 16-byte copies; 4 planes per sweep
+  const int seg = (t & 31) * 4, kofs = t >> 5;
+  if (seg < np) {
+    for (int k = kofs; k < D; k += 4) {
+      cp_async16(sl + k * kHeadPix + seg, lg + (long long)k * HW + seg);
+      if (per_pixel) cp_async16(sh + k * kHeadPix + seg, hg + (long long)k * HW + seg);
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (t >= np) return;
+  const float* hb = hyp + (long long)b * D;  // [B,D] hypotheses
   float m = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < MAXD; ++k) {
-    if (k < D) {
-      e[k] = __ldcs(lg + (long long)k * HW);
-      m = fmaxf(m, e[k]);
-    }
-  }
+  for (int k = 0; k < D; ++k) m = fmaxf(m, sl[k * kHeadPix + t]);
   float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < MAXD; ++k) {
-    if (k < D) {
-      e[k] = expf(e[k] - m);
-      s += e[k];
-    }
+  for (int k = 0; k < D; ++k) {
+    const float e = expf(sl[k * kHeadPix + t] - m);
+    sl[k * kHeadPix + t] = e;
+    s += e;
   }
-  const float* hp = per_pixel ? hyp + b * D * HW + p : hyp + b * D;
-  const long long hs = per_pixel ? HW : 1;
-  float dsum = 0.f, isum = 0.f, d2sum = 0.f;
-  float* pr = prob ? prob + b * D * HW + p : nullptr;
-  // first sweep: probabilities, expected depth and expected index
-#pragma unroll
-  for (int k = 0; k < MAXD; ++k) {
-    if (k < D) {
-      float pk = e[k] / s;
-      e[k] = pk;
-      float dk = __ldg(hp + k * hs);
-      dsum += pk * dk;
-      isum += pk * (float)k;
-      if (pr) __stcs(pr + (long long)k * HW, pk);
-    }
+  float dsum = 0.f, isum = 0.f;
+  float* pr = prob ? prob + (long long)b * D * HW + p0 + t : nullptr;
+  for (int k = 0; k < D; ++k) {
+    const float pk = sl[k * kHeadPix + t] / s;
+    sl[k * kHeadPix + t] = pk;
+    const float dk = per_pixel ? sh[k * kHeadPix + t] : __ldg(hb + k);
+    dsum += pk * dk;
+    isum += pk * (float)k;
+    if (pr) __stcs(pr + (long long)k * HW, pk);
   }
-  // second sweep: hypothesis variance about the expected depth (hypotheses are L1/L2 hits)
-#pragma unroll
-  for (int k = 0; k < MAXD; ++k) {
-    if (k < D) {
-      float dk = __ldg(hp + k * hs);
-      float t = dk - dsum;
-      d2sum += (t * t) * e[k];
-    }
+  float d2sum = 0.f;
+  for (int k = 0; k < D; ++k) {
+    const float dk = per_pixel ? sh[k * kHeadPix + t] : __ldg(hb + k);
+    const float df = dk - dsum;
+    d2sum += (df * df) * sl[k * kHeadPix + t];
   }
   long long idx = (long long)isum;  // .long() truncation, reference cas_mvsnet.py:116
   idx = idx < 0 ? 0 : (idx > D - 1 ? D - 1 : idx);
   float c = 0.f;
-#pragma unroll
-  for (int k = 0; k < MAXD; ++k) {
-    if (k < D) {
-      if (k >= idx - 1 && k <= idx + 2) c += e[k];
-    }
-  }
-  depth[pix] = dsum;
-  conf[pix] = c;
-  var[pix] = 3.f * sqrtf(d2sum);
+  for (int k = (int)idx - 1; k <= (int)idx + 2; ++k)
+    if (k >= 0 && k < D) c += sl[k * kHeadPix + t];
+  const long long o = (long long)b * HW + p0 + t;
+  depth[o] = dsum;
+  conf[o] = c;
+  var[o] = 3.f * sqrtf(d2sum);
 }
 
 // Any D: three passes over the logits column (re-reads are L2 hits).
@@ -148,17 +152,17 @@ extern "C" int damvs_softmax_regress_fwd(const float* logits, const float* depth
   long long HW = (long long)H * W, total = HW * B;
   cudaStream_t st = (cudaStream_t)stream;
   unsigned blocks = (unsigned)((total + 255) / 256);
-#define LAUNCH(MAXD) \
-  head_reg_kernel<MAXD><<<blocks, 256, 0, st>>>(logits, depth_hyp, prob, depth, conf, var, D, HW, total, per_pixel_hyp)
-  if (D <= 8) LAUNCH(8);
-  else if (D <= 16) LAUNCH(16);
-  else if (D <= 32) LAUNCH(32);
-  else if (D <= 48) LAUNCH(48);
-  else if (D <= 64) LAUNCH(64);
-  else
+  const bool aligned = (HW % 4 == 0) && aligned16(logits) && aligned16(depth_hyp) && B <= 65535;
+  if (D <= 64 && aligned) {
+    const size_t smem = (size_t)2 * D * kHeadPix * sizeof(float);
+    if (smem > 48 * 1024)
+      DAMVS_CUDA_OK(cudaFuncSetAttribute(head_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((HW + kHeadPix - 1) / kHeadPix), B);
+    head_staged_kernel<<<grid, kHeadPix, smem, st>>>(logits, depth_hyp, prob, depth, conf, var, D, HW, per_pixel_hyp);
+  } else {
     head_stream_kernel<<<blocks, 256, 0, st>>>(logits, depth_hyp, prob, depth, conf, var, D, HW, total,
                                                per_pixel_hyp);
-#undef LAUNCH
+  }
   DAMVS_LAUNCH_OK("head kernel");
   return DAMVS_OK;
 }
