@@ -228,11 +228,9 @@ def run_ours(args):
     barrier()
     launches = (_lib.launch_count() - l0) // steps
     clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = ms.item()
-    value = world * steps / (total_ms / 1e3)
+    from damvsnet_b200 import sharding
+    total_views, total_ms = sharding.reduce_throughput(steps, e0.elapsed_time(e1), dev)   # sum of views, max of device time
+    value = total_views / (total_ms / 1e3)
 
     # ---- end to end: host buffers in, host results out, copies inside the timed region
     e2e = None
@@ -247,10 +245,8 @@ def run_ours(args):
             runner.run_host(pinned)
         e1.record()
         barrier()
-        ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * e_steps / (ms2.item() / 1e3), "unit": UNIT,
+        e_views, e_ms = sharding.reduce_throughput(e_steps, e0.elapsed_time(e1), dev)
+        e2e = {"value": e_views / (e_ms / 1e3), "unit": UNIT,
                "h2d_bytes_per_step": runner.h2d_bytes(host_stages), "d2h_bytes_per_step": runner.d2h_bytes(host_stages),
                "steps": e_steps, "api": "HotPathRunner.run_host (pinned host features/proj/hypotheses in; depth, confidence, "
                                         "variance of 3 stages out)"}
