@@ -44,6 +44,7 @@ class HotPathRunner:
         self.cost_regularization.to(self.device)
         self._copy_stream = None
         self._host_out = None
+        self._graphs = {}
 
     # ------------------------------------------------------------------ device-resident
     @torch.no_grad()
@@ -54,6 +55,32 @@ class HotPathRunner:
     @torch.no_grad()
     def run_device(self, stages: Sequence[StageInput]) -> List[Dict[str, torch.Tensor]]:
         return [self.run_stage(i, f, p, d) for i, (f, p, d) in enumerate(stages)]
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    @staticmethod
+    def _signature(stages: Sequence[StageInput]):
+        return tuple((tuple(f.data_ptr() for f in fs), p.data_ptr(), d.data_ptr(), tuple(d.shape), fs[0].shape[1])
+                     for fs, p, d in stages)
+
+    @torch.no_grad()
+    def run_device_graphed(self, stages: Sequence[StageInput]) -> List[Dict[str, torch.Tensor]]:
+        """Same result as run_device, replayed from a CUDA graph captured on first use for these input
+        buffers (pointers and shapes are baked in: callers refill the same tensors between calls).
+        One graph launch replaces ~60 kernel launches + ~70 small torch ops of host work per view."""
+        from . import ops
+        key = (self._signature(stages), ops.get_precision(), ops._POLICY["conv_impl"])
+        hit = self._graphs.get(key)
+        if hit is None:
+            # warm-up outside capture: weight packing synchronises and fills the per-module caches
+            self.run_device(stages)
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                outs = self.run_device(stages)
+            hit = (g, outs)
+            self._graphs[key] = hit
+        hit[0].replay()
+        return hit[1]
 
     # ------------------------------------------------------------------ host buffers
     @staticmethod
