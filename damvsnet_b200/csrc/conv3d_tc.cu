@@ -72,6 +72,7 @@ struct TcParams {
   int B, G, Din, Hin, Win, Dout, Hout, Wout;
   int out_G, out_g0;  // output volume's group count and first group written by this launch
   int n0, Cout, relu, plain_out, niter, nsteps, nslots;
+  int tiles_x, tiles_y, ntiles;  // persistent CTAs walk tiles blockIdx.x, blockIdx.x + gridDim.x, ...
   unsigned long long* trace;  // development aid: per-CTA event timestamps (null in production)
 };
 
@@ -96,7 +97,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define TRACE(slot_)                                                                                              \
   do {                                                                                                            \
-    if (P.trace) P.trace[((size_t)(blockIdx.y * gridDim.x + blockIdx.x)) * 64 + (slot_)] = gtime();                \
+    if (P.trace) P.trace[((size_t)blockIdx.x) * 64 + (slot_)] = gtime();                \
   } while (0)
 
 __device__ __forceinline__ float shfl_dn(uint32_t v, int d) { return __uint_as_float(__shfl_down_sync(0xffffffffu, v, d)); }
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
   const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(P.blob);
   const int nsteps = P.nsteps;
   if (hdr->magic != kMagic || hdr->mode != MODE || hdr->CP != CP || hdr->nsteps != nsteps) {
-    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0)
+    if (threadIdx.x == 0 && blockIdx.x == 0)
       printf("damvs: packed conv weights were built for another layer type (mode %d CP %d, kernel mode %d CP %d)\n", hdr->mode, hdr->CP, MODE, CP);
     __trap();
   }
@@ -223,9 +224,11 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.z;
-  const int ty0 = blockIdx.y * TH;     // tile origin (output coords for S1/S2, input coords for T)
-  const int tx0 = blockIdx.x * G_::TW;
+  // tile -> (batch item, tile origin); origins are output coords for S1/S2, input coords for T
+#define TILE_COORDS(tile_)                                               \
+  const int b = (tile_) / (P.tiles_x * P.tiles_y);                       \
+  const int ty0 = (((tile_) / P.tiles_x) % P.tiles_y) * TH;              \
+  const int tx0 = ((tile_) % P.tiles_x) * G_::TW;
 
   if (threadIdx.x == 0) TRACE(0);
   // ---- one-time setup ------------------------------------------------------------------------
@@ -263,6 +266,8 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
       const int nplanes = (niter - 1) * G_::adv + G_::span;
       const uint32_t bytes = (uint32_t)(patch0_bytes + patch1_bytes);
       int slot = 0, round = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      TILE_COORDS(tile)
       for (int k = 0; k < nplanes; ++k) {
         if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
         mbar_arrive_expect_tx(&full[slot], bytes);
@@ -278,26 +283,30 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
         }
         if (++slot == nslots) { slot = 0; ++round; }
       }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp walks the (uniform) program, one elected lane issues =====
     const bool leader = elect_one();
     const uint32_t a_base16 = smem_u32(sA) >> 4, b_base16 = smem_u32(sB) >> 4;
     const uint32_t slot16 = (uint32_t)slot_stride >> 4;
-    int wait_slot = 0, wait_round = 0, next_wait = 0;       // full-barrier cursor
+    int wait_slot = 0, wait_round = 0;                       // full-barrier cursor (runs across tiles)
     int base_slot = 0;                                       // slot of the first plane of this iteration
-    for (int it = 0; it < niter; ++it) {
+    int acc_n = 0;                                           // accumulator buffers handed to the epilogue so far
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+    int next_wait = 0;
+    for (int it = 0; it < niter; ++it, ++acc_n) {
       const int need = it * G_::adv + G_::span - 1;
       while (next_wait <= need) {
         mbar_wait(&full[wait_slot], wait_round & 1);
         ++next_wait;
         if (++wait_slot == nslots) { wait_slot = 0; ++wait_round; }
       }
-      if (leader && it < 12) TRACE(4 + it);
-      const int buf = NBUF == 2 ? (it & 1) : 0;
-      if (it >= NBUF) mbar_wait(&tmem_empty[buf], (NBUF == 2 ? ((it >> 1) - 1) : (it - 1)) & 1);
+      if (leader && acc_n < 12) TRACE(4 + acc_n);
+      const int buf = NBUF == 2 ? (acc_n & 1) : 0;
+      if (acc_n >= NBUF) mbar_wait(&tmem_empty[buf], (NBUF == 2 ? ((acc_n >> 1) - 1) : (acc_n - 1)) & 1);
       tc_fence_after();
-      if (leader && it < 12) TRACE(16 + it);
+      if (leader && acc_n < 12) TRACE(16 + acc_n);
       const uint32_t dbase = tmem_base + buf * ACC_COLS;
       int s1 = base_slot + 1; if (s1 >= nslots) s1 -= nslots;
       int s2 = base_slot + 2; if (s2 >= nslots) s2 -= nslots;
@@ -316,6 +325,17 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
       base_slot += G_::adv; if (base_slot >= nslots) base_slot -= nslots;
       __syncwarp();
     }
+    // the last span - adv planes of the tile were only read, never released, by the iteration loop
+    if (leader) {
+#pragma unroll
+      for (int a = 0; a < G_::span - G_::adv; ++a) {
+        int rs = base_slot + a; if (rs >= nslots) rs -= nslots;
+        mma_commit(&empty[rs]);
+      }
+    }
+    base_slot += G_::span - G_::adv; if (base_slot >= nslots) base_slot -= nslots;
+    __syncwarp();
+    }
   } else {
     // ===== epilogue: 8 warps; warp w owns TMEM lanes 32*(w%4).., the two warps of a lane quarter split the
     // work units (chunks, or channel groups, or parity classes) of an iteration between them =====
@@ -323,8 +343,11 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
     constexpr int CPG = CP / 8;
     const int ngroups = P.plain_out ? 1 : min(CPG, (P.Cout - P.n0 + 7) / 8);   // real (non-padding) channel groups
     const long long HWo = (long long)P.Hout * P.Wout;
-    for (int it = 0; it < niter; ++it) {
-      const int buf = NBUF == 2 ? (it & 1) : 0;
+    int acc_n = 0;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+    TILE_COORDS(tile)
+    for (int it = 0; it < niter; ++it, ++acc_n) {
+      const int buf = NBUF == 2 ? (acc_n & 1) : 0;
       const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS;
       if (MODE == MODE_T) {
         // units: (class pdh in {2*half, 2*half+1}) x chunk x group; each unit = two adjacent output voxels (x parity)
@@ -350,9 +373,9 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
             sk[u][0] = sk[u][1] = make_uint4(0, 0, 0, 0);
           }
         }
-        mbar_wait(&tmem_full[buf], (NBUF == 2 ? (it >> 1) : it) & 1);
+        mbar_wait(&tmem_full[buf], (NBUF == 2 ? (acc_n >> 1) : acc_n) & 1);
         tc_fence_after();
-        if (warp == 2 && lane == 0 && it < 12) TRACE(28 + it);
+        if (warp == 2 && lane == 0 && acc_n < 12) TRACE(28 + acc_n);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int k = u / (MC * CPG), c = (u / CPG) % MC, ng = u % CPG;
@@ -402,9 +425,9 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
           else offs[u] = g8_offset(b, P.out_g0 + ng, it, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
           sk[u] = (P.skip && valid[u] && ng < ngroups) ? __ldg(reinterpret_cast<const uint4*>(P.skip + offs[u])) : make_uint4(0, 0, 0, 0);
         }
-        mbar_wait(&tmem_full[buf], (NBUF == 2 ? (it >> 1) : it) & 1);
+        mbar_wait(&tmem_full[buf], (NBUF == 2 ? (acc_n >> 1) : acc_n) & 1);
         tc_fence_after();
-        if (warp == 2 && lane == 0 && it < 12) TRACE(28 + it);
+        if (warp == 2 && lane == 0 && acc_n < 12) TRACE(28 + acc_n);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int c = MC >= 2 ? half * (MC / 2) + u / CPG : 0;
@@ -442,9 +465,11 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-      if (warp == 2 && lane == 0 && it < 12) TRACE(40 + it);
+      if (warp == 2 && lane == 0 && acc_n < 12) TRACE(40 + acc_n);
+    }
     }
   }
+#undef TILE_COORDS
 
   tc_fence_before();
   __syncthreads();
@@ -657,8 +682,7 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   int nslots = (int)((kSmemBudget - fx) / sb);
   const int nplanes = (P.niter - 1) * G_::adv + G_::span;
   if (nslots > kMaxSlots) nslots = kMaxSlots;
-  if (nslots > nplanes) nslots = nplanes;
-  if (nslots < G_::span + 1 && nslots < nplanes) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: ring does not fit");
+  if (nslots < G_::span + 1) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: ring does not fit");
   // leave room for a second CTA per SM when a deep ring is not needed
   while (nslots > G_::span + 2 && fx + (size_t)nslots * sb > kSmemBudget / 2) --nslots;
   P.nslots = nslots;
@@ -667,10 +691,22 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int TH = 4 * MC;
   const int tiles_h = MODE == MODE_T ? d->Hin : P.Hout, tiles_w = MODE == MODE_T ? d->Win : P.Wout;
-  dim3 grid((tiles_w + G_::TW - 1) / G_::TW, (tiles_h + TH - 1) / TH, d->B);
+  P.tiles_x = (tiles_w + G_::TW - 1) / G_::TW;
+  P.tiles_y = (tiles_h + TH - 1) / TH;
+  P.ntiles = P.tiles_x * P.tiles_y * d->B;
+  // persistent grid: as many CTAs as fit at once (shared memory, TMEM columns, registers)
+  int occ = 0;
+  DAMVS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 320, smem));
+  constexpr int ACC = Geo<MODE>::ncls * MC * 3 * CP;
+  constexpr int NEEDC = (2 * ACC <= 512 ? 2 : 1) * ACC;
+  constexpr int TCOLS = NEEDC <= 32 ? 32 : NEEDC <= 64 ? 64 : NEEDC <= 128 ? 128 : NEEDC <= 256 ? 256 : 512;
+  occ = std::max(1, std::min(occ, 512 / TCOLS));
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  dim3 grid((unsigned)std::min(P.ntiles, occ * num_sms), 1, 1);
   const char* tr = getenv("DAMVS_TC_TRACE");
   if (tr) {  // development aid: timestamps of a few CTAs, printed to stderr (synchronises!)
-    const size_t n = (size_t)grid.x * grid.y * 64;
+    const size_t n = (size_t)grid.x * 64;
     unsigned long long* dbuf;
     cudaMalloc(&dbuf, n * 8);
     cudaMemset(dbuf, 0, n * 8);
@@ -683,8 +719,8 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
     P.trace = nullptr;
     unsigned long long t0 = ~0ull, t1 = 0;
     for (size_t c = 0; c < n / 64; ++c) { if (h[c * 64]) t0 = std::min(t0, h[c * 64]); t1 = std::max(t1, h[c * 64 + 2]); }
-    fprintf(stderr, "[tc trace] mode %d CP %d MC %d G %d grid %ux%u niter %d nslots %d smem %zu: kernel span %.1f us\n", MODE, CP, MC, G, grid.x,
-            grid.y, P.niter, nslots, smem, (t1 - t0) / 1e3);
+    fprintf(stderr, "[tc trace] mode %d CP %d MC %d G %d grid %u tiles %d niter %d nslots %d smem %zu: kernel span %.1f us\n", MODE, CP, MC, G, grid.x,
+            P.ntiles, P.niter, nslots, smem, (t1 - t0) / 1e3);
     const size_t picks[3] = {0, n / 64 / 2, n / 64 - 1};
     for (size_t pi = 0; pi < 3; ++pi) {
       const unsigned long long* e = &h[picks[pi] * 64];
