@@ -684,7 +684,7 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   if (nslots > kMaxSlots) nslots = kMaxSlots;
   if (nslots < G_::span + 1) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: ring does not fit");
   // leave room for a second CTA per SM when a deep ring is not needed
-  while (nslots > G_::span + 2 && fx + (size_t)nslots * sb > kSmemBudget / 2) --nslots;
+  while (nslots > G_::span + 1 && fx + (size_t)nslots * sb + 1024 > kSmemBudget / 2) --nslots;
   P.nslots = nslots;
   const size_t smem = fx + (size_t)nslots * sb;
   auto kern = conv3d_tc_kernel<MODE, CP, MC, G>;
@@ -695,8 +695,11 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   P.tiles_y = (tiles_h + TH - 1) / TH;
   P.ntiles = P.tiles_x * P.tiles_y * d->B;
   // persistent grid: as many CTAs as fit at once (shared memory, TMEM columns, registers)
-  int occ = 0;
-  DAMVS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 320, smem));
+  DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  cudaFuncAttributes fa;
+  DAMVS_CUDA_OK(cudaFuncGetAttributes(&fa, kern));
+  const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 320;
+  int occ = std::min({(int)((228 * 1024) / (smem + fa.sharedSizeBytes + 1024)), 65536 / regs_per_cta, 2048 / 320});
   constexpr int ACC = Geo<MODE>::ncls * MC * 3 * CP;
   constexpr int NEEDC = (2 * ACC <= 512 ? 2 : 1) * ACC;
   constexpr int TCOLS = NEEDC <= 32 ? 32 : NEEDC <= 64 ? 64 : NEEDC <= 128 ? 128 : NEEDC <= 256 ? 256 : 512;

@@ -25,6 +25,8 @@
 // Sampling semantics are the reference's, quirk included:
 // the grid is normalised with (W-1)/2 but sampled with align_corners=False, no
 // z>0 mask, no epsilon in the perspective divide, zero padding per tap.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace damvs {
@@ -132,12 +134,14 @@ __device__ __forceinline__ float2 splat(float a) { return make_float2(a, a); }
 struct Tap8 {
   float2 v[4];
 };
+// one 256-bit read-only load (sm_100 LDG.E.256): the 8 channels of a tap in a single request, so the
+// C/8 lanes of a pixel fetch its C*4-byte tap segment with one L1 wavefront per 128-byte line
 __device__ __forceinline__ Tap8 load_tap8(const float* p) {
   Tap8 t;
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  t.v[0] = make_float2(a.x, a.y); t.v[1] = make_float2(a.z, a.w);
-  t.v[2] = make_float2(b.x, b.y); t.v[3] = make_float2(b.z, b.w);
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(t.v[0].x), "=f"(t.v[0].y), "=f"(t.v[1].x), "=f"(t.v[1].y), "=f"(t.v[2].x), "=f"(t.v[2].y),
+                 "=f"(t.v[3].x), "=f"(t.v[3].y)
+               : "l"(p));
   return t;
 }
 
@@ -150,7 +154,7 @@ __device__ __forceinline__ Tap8 load_tap8(const float* p) {
 //     block most of the time (sub-pixel steps along the epipolar line): the taps stay in registers and are
 //     only re-fetched when the block changes;
 //   * the per-channel math runs on packed fp32x2 instructions.
-template <int C, int MODE, typename OutT, int DCH>
+template <int C, int MODE, typename OutT, int DCH, bool PF>
 __global__ void __launch_bounds__(128) warp_agg_kernel(const WarpAggParams P) {
   constexpr int LPP = C / 8;     // lanes per pixel
   constexpr int PPW = 32 / LPP;  // pixels per warp (along x)
@@ -267,6 +271,18 @@ __global__ void __launch_bounds__(128) warp_agg_kernel(const WarpAggParams P) {
             t11 = load_tap8(p + (long long)W * C + C);
             cur = off;
           }
+          if (PF && j + 1 < DCH) {  // pull the next hypothesis' tap lines towards L1 while this one is blended
+            const int offn = LPP > 1 ? s_fo[warp][pw][j + 1] : fp[j + 1 < DCH ? j + 1 : j].off;
+            if (offn != off) {
+              const float* pn = img + offn;
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pn));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + (long long)W * C));
+              if (C * 4 * 2 > 128 || (((size_t)pn & 127) + C * 8 > 128)) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + C));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pn + (long long)W * C + C));
+              }
+            }
+          }
           const float2 a00 = splat(fwt.x), a01 = splat(fwt.y), a10 = splat(fwt.z), a11 = splat(fwt.w);
           float2 wv[4];
 #pragma unroll
@@ -355,10 +371,19 @@ template <int C, int MODE>
 static int launch_warp_agg(const WarpAggParams& P, int out_dtype, cudaStream_t st) {
   constexpr int TW = 32 / (C / 8), TH = 4, DCH = 4;
   dim3 grid((P.W + TW - 1) / TW, (P.H + TH - 1) / TH, P.B);
+  static const int cfg = getenv("DAMVS_WARP_CFG") ? atoi(getenv("DAMVS_WARP_CFG")) : 0;   // development knob
   if (out_dtype == DAMVS_F32)
-    warp_agg_kernel<C, MODE, float, DCH><<<grid, 128, 0, st>>>(P);
+    warp_agg_kernel<C, MODE, float, DCH, false><<<grid, 128, 0, st>>>(P);
+  else if (cfg == 1)
+    warp_agg_kernel<C, MODE, __nv_bfloat16, 4, true><<<grid, 128, 0, st>>>(P);
+  else if (cfg == 2)
+    warp_agg_kernel<C, MODE, __nv_bfloat16, 2, false><<<grid, 128, 0, st>>>(P);
+  else if (cfg == 3)
+    warp_agg_kernel<C, MODE, __nv_bfloat16, 2, true><<<grid, 128, 0, st>>>(P);
+  else if (cfg == 4)
+    warp_agg_kernel<C, MODE, __nv_bfloat16, 8, false><<<grid, 128, 0, st>>>(P);
   else
-    warp_agg_kernel<C, MODE, __nv_bfloat16, DCH><<<grid, 128, 0, st>>>(P);
+    warp_agg_kernel<C, MODE, __nv_bfloat16, DCH, false><<<grid, 128, 0, st>>>(P);
   DAMVS_LAUNCH_OK("warp_agg kernel");
   return DAMVS_OK;
 }
@@ -378,12 +403,12 @@ extern "C" int damvs_warp_agg_fwd(const float* ref_nhwc, const float* const* src
   DAMVS_REQUIRE(mode == DAMVS_AGG_VARIANCE || mode == DAMVS_AGG_ADAPTIVE, "warp_agg: bad mode %d", mode);
   DAMVS_REQUIRE(mode == DAMVS_AGG_VARIANCE || wnet != nullptr, "warp_agg: adaptive mode needs wnet");
   DAMVS_REQUIRE(out_dtype == DAMVS_F32 || out_dtype == DAMVS_BF16, "warp_agg: bad out_dtype %d", out_dtype);
-  DAMVS_REQUIRE(aligned16(ref_nhwc) && aligned16(out_vol), "warp_agg: ref/out must be 16-byte aligned");
+  DAMVS_REQUIRE((reinterpret_cast<uintptr_t>(ref_nhwc) & 31u) == 0 && aligned16(out_vol), "warp_agg: ref must be 32-byte, out 16-byte aligned");
   WarpAggParams P;
   P.ref = ref_nhwc;
   for (int v = 0; v < kMaxSrc; ++v) P.src[v] = v < n_src ? src_nhwc[v] : nullptr;
   for (int v = 0; v < n_src; ++v)
-    DAMVS_REQUIRE(src_nhwc[v] && aligned16(src_nhwc[v]), "warp_agg: src[%d] null or not 16-byte aligned", v);
+    DAMVS_REQUIRE(src_nhwc[v] && (reinterpret_cast<uintptr_t>(src_nhwc[v]) & 31u) == 0, "warp_agg: src[%d] null or not 32-byte aligned", v);
   P.rot_trans = rot_trans; P.hyp = depth_hyp; P.wnet = wnet; P.out = out_vol;
   P.B = B; P.n_src = n_src; P.D = D; P.H = H; P.W = W; P.per_pixel = per_pixel_hyp;
   cudaStream_t st = (cudaStream_t)stream;

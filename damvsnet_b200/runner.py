@@ -99,15 +99,18 @@ class HotPathRunner:
         return sum(3 * dv.shape[0] * dv.shape[2] * dv.shape[3] * 4 for _, _, dv in stages)
 
     @torch.no_grad()
-    def run_host(self, stages: Sequence[StageInput]) -> List[Dict[str, torch.Tensor]]:
-        """Host tensors in, pinned host tensors (depth, photometric_confidence, variance per stage) out.
-        Returns after the results have landed on the host."""
+    def submit_host(self, stages: Sequence[StageInput]) -> "HostTicket":
+        """Enqueue one view whose inputs live in (pinned) host memory: H2D on the copy stream, the three stages
+        on the compute stream (stage s waits only for its own inputs), D2H of depth / confidence / variance on
+        the readback stream.  Returns immediately; `collect` waits.  Submitting view i+1 before collecting
+        view i overlaps its upload with view i's kernels."""
         dev = self.device
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
+            self._d2h_stream = torch.cuda.Stream(device=dev)
+            self._host_pool = []
         compute = torch.cuda.current_stream(dev)
-        copy = self._copy_stream
-        copy.wait_stream(compute)
+        copy, d2h = self._copy_stream, self._d2h_stream
         uploaded, ready = [], []
         with torch.cuda.stream(copy):
             for feats, proj, dv in stages:
@@ -118,21 +121,55 @@ class HotPathRunner:
                 ev.record(copy)
                 uploaded.append((dfe, dpr, ddv))
                 ready.append(ev)
-        if self._host_out is None or len(self._host_out) != len(stages) or any(
-                o["depth"].shape != (dv.shape[0], dv.shape[2], dv.shape[3]) for o, (_, _, dv) in zip(self._host_out, stages)):
-            self._host_out = [{k: torch.empty((dv.shape[0], dv.shape[2], dv.shape[3]), dtype=torch.float32).pin_memory()
-                               for k in ("depth", "photometric_confidence", "variance")} for _, _, dv in stages]
-        outs = []
+        shapes = [(dv.shape[0], dv.shape[2], dv.shape[3]) for _, _, dv in stages]
+        host = None
+        for i, cand in enumerate(self._host_pool):
+            if [tuple(o["depth"].shape) for o in cand] == shapes:
+                host = self._host_pool.pop(i)
+                break
+        if host is None:
+            host = [{k: torch.empty(sh, dtype=torch.float32).pin_memory()
+                     for k in ("depth", "photometric_confidence", "variance")} for sh in shapes]
         for i, ((dfe, dpr, ddv), ev) in enumerate(zip(uploaded, ready)):
             compute.wait_event(ev)
             for t in dfe + [dpr, ddv]:
                 t.record_stream(compute)
             out = self.run_stage(i, dfe, dpr, ddv)
-            for k, host in self._host_out[i].items():
-                host.copy_(out[k], non_blocking=True)
-            outs.append(out)
-        compute.synchronize()
-        return self._host_out
+            done = torch.cuda.Event()
+            done.record(compute)
+            d2h.wait_event(done)
+            with torch.cuda.stream(d2h):
+                for k, h in host[i].items():
+                    out[k].record_stream(d2h)
+                    h.copy_(out[k], non_blocking=True)
+        fin = torch.cuda.Event()
+        fin.record(d2h)
+        return HostTicket(host, fin)
+
+    def collect(self, ticket: "HostTicket") -> List[Dict[str, torch.Tensor]]:
+        """Wait for a submitted view; the returned pinned host tensors are recycled by a later submit_host
+        once `release` is called (or the ticket is dropped)."""
+        ticket.event.synchronize()
+        return ticket.host
+
+    def release(self, ticket: "HostTicket") -> None:
+        self._host_pool.append(ticket.host)
+
+    @torch.no_grad()
+    def run_host(self, stages: Sequence[StageInput]) -> List[Dict[str, torch.Tensor]]:
+        """Host tensors in, pinned host tensors (depth, photometric_confidence, variance per stage) out.
+        Returns after the results have landed on the host."""
+        if getattr(self, "_last_ticket", None) is not None:
+            self.release(self._last_ticket)      # buffers handed out by the previous call are recycled now
+        t = self.submit_host(stages)
+        self._last_ticket = t
+        return self.collect(t)
+
+
+class HostTicket:
+    def __init__(self, host, event):
+        self.host = host
+        self.event = event
 
 
 def make_workload(height: int, width: int, nviews: int, ndepths: Sequence[int], batch: int = 1, seed: int = 0,
