@@ -109,17 +109,33 @@ class HotPathRunner:
             self._copy_stream = torch.cuda.Stream(device=dev)
             self._d2h_stream = torch.cuda.Stream(device=dev)
             self._host_pool = []
+            self._dev_in = [None, None]
+            self._set_done = [None, None]
+            self._submits = 0
         compute = torch.cuda.current_stream(dev)
         copy, d2h = self._copy_stream, self._d2h_stream
+        # two persistent sets of device input buffers (no allocator traffic, hence no implicit device syncs):
+        # set k is overwritten only after the kernels that last read it have finished
+        bset = self._submits % 2
+        self._submits += 1
+        if self._dev_in[bset] is None or [[tuple(t.shape) for t in st[0]] + [tuple(st[1].shape), tuple(st[2].shape)] for st in self._dev_in[bset]] != \
+                [[tuple(f.shape) for f in feats] + [tuple(proj.shape), tuple(dv.shape)] for feats, proj, dv in stages]:
+            self._dev_in[bset] = [([torch.empty(f.shape, dtype=f.dtype, device=dev) for f in feats],
+                                torch.empty(proj.shape, dtype=proj.dtype, device=dev),
+                                torch.empty(dv.shape, dtype=dv.dtype, device=dev)) for feats, proj, dv in stages]
+            self._set_done[bset] = None
+        if self._set_done[bset] is not None:
+            copy.wait_event(self._set_done[bset])
         uploaded, ready = [], []
         with torch.cuda.stream(copy):
-            for feats, proj, dv in stages:
-                dfe = [f.to(dev, non_blocking=True) for f in feats]
-                dpr = proj.to(dev, non_blocking=True)
-                ddv = dv.to(dev, non_blocking=True)
+            for (feats, proj, dv), (bfe, bpr, bdv) in zip(stages, self._dev_in[bset]):
+                for src, dst in zip(feats, bfe):
+                    dst.copy_(src, non_blocking=True)
+                bpr.copy_(proj, non_blocking=True)
+                bdv.copy_(dv, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
-                uploaded.append((dfe, dpr, ddv))
+                uploaded.append((bfe, bpr, bdv))
                 ready.append(ev)
         shapes = [(dv.shape[0], dv.shape[2], dv.shape[3]) for _, _, dv in stages]
         host = None
@@ -132,8 +148,6 @@ class HotPathRunner:
                      for k in ("depth", "photometric_confidence", "variance")} for sh in shapes]
         for i, ((dfe, dpr, ddv), ev) in enumerate(zip(uploaded, ready)):
             compute.wait_event(ev)
-            for t in dfe + [dpr, ddv]:
-                t.record_stream(compute)
             out = self.run_stage(i, dfe, dpr, ddv)
             done = torch.cuda.Event()
             done.record(compute)
@@ -142,6 +156,9 @@ class HotPathRunner:
                 for k, h in host[i].items():
                     out[k].record_stream(d2h)
                     h.copy_(out[k], non_blocking=True)
+        used = torch.cuda.Event()
+        used.record(compute)
+        self._set_done[bset] = used
         fin = torch.cuda.Event()
         fin.record(d2h)
         return HostTicket(host, fin)
