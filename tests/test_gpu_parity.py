@@ -287,3 +287,58 @@ def test_depthnet_bf16_within_stated_bound(dm, mode, stage):
     assert (out["prob_volume"].cpu() - st["prob_volume"]).abs().max().item() < 0.1
     cerr = (out["photometric_confidence"].cpu() - st["photometric_confidence"]).abs()
     assert torch.quantile(cerr.flatten(), 0.99).item() < 6e-2
+
+
+# ---------------------------------------------------------------- other configurations of BASELINE.json
+@pytest.mark.parametrize("stage,D", [(0, 64), (1, 32), (2, 8)])
+def test_depthnet_batch2_seven_views_default_depths(dm, stage, D):
+    """B = 2, N = 7 (Tanks-and-Temples view count), the reference's default 64/32/8 hypothesis counts
+    (train.py:63), ragged-free small extent: fp32 path against the oracle."""
+    from damvsnet_b200 import synthetic
+    sd = synthetic.hot_path_state_dict(seed=21)
+    feats, pm, dv = synthetic.make_stage_inputs(stage, 2, 7, 64, 96, D, seed=9)
+    net, cr = _build_net(dm, sd, stage, "adaptive")
+    want = O.depthnet_forward(stage, feats, pm, dv, sd, "adaptive")
+    with dm.precision("fp32"), torch.no_grad():
+        out = net(stage, [f.to(dev()) for f in feats], pm.to(dev()), dv.to(dev()), D, cr)
+    rel = _rel(out["depth"].cpu(), want["depth"])
+    assert rel.max().item() < 1e-4, rel.max().item()
+    assert (out["prob_volume"].cpu() - want["prob_volume"]).abs().max() < 2e-3
+    with dm.precision("bf16"), torch.no_grad():
+        out16 = net(stage, [f.to(dev()) for f in feats], pm.to(dev()), dv.to(dev()), D, cr)
+    span = (dv.max(1).values - dv.min(1).values).clamp_min(1e-3)
+    nrm = (out16["depth"].cpu() - want["depth"]).abs() / span
+    assert nrm.median().item() < 2.5e-3 and torch.quantile(nrm.flatten(), 0.99).item() < 3e-2
+
+
+def test_runner_graph_replay_matches_eager(dm):
+    from damvsnet_b200 import synthetic
+    from damvsnet_b200.runner import HotPathRunner, make_workload
+    sd = synthetic.hot_path_state_dict(seed=3)
+    runner = HotPathRunner(sd, device=dev())
+    stages = make_workload(64, 96, 3, [16, 8, 8], seed=2, device=dev())
+    eager = [{k: v.clone() for k, v in o.items()} for o in runner.run_device(stages)]
+    for _ in range(2):
+        replay = runner.run_device_graphed(stages)
+    torch.cuda.synchronize()
+    for a, b in zip(eager, replay):
+        for k in ("depth", "photometric_confidence", "variance", "prob_volume"):
+            assert torch.equal(a[k], b[k]), k
+
+
+def test_runner_host_pipeline_matches_device(dm):
+    from damvsnet_b200 import synthetic
+    from damvsnet_b200.runner import HotPathRunner, make_workload
+    sd = synthetic.hot_path_state_dict(seed=3)
+    runner = HotPathRunner(sd, device=dev())
+    host = make_workload(64, 96, 3, [16, 8, 8], seed=2)
+    ref = runner.run_device([([f.to(dev()) for f in fs], p.to(dev()), d.to(dev())) for fs, p, d in host])
+    pinned = runner.pin_stages(host)
+    t1 = runner.submit_host(pinned)
+    t2 = runner.submit_host(pinned)
+    for t in (t1, t2):
+        got = runner.collect(t)
+        for a, b in zip(ref, got):
+            for k in ("depth", "photometric_confidence", "variance"):
+                assert torch.equal(a[k].cpu(), b[k]), k
+        runner.release(t)
