@@ -369,6 +369,10 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
           if (P.skip && valid[c] && ng < ngroups) {
             sk[u][0] = __ldg(reinterpret_cast<const uint4*>(P.skip + offs[u]));
             sk[u][1] = __ldg(reinterpret_cast<const uint4*>(P.skip + offs[u] + 8));
+            // the same voxels two output planes further are next iteration's skip operands: start them towards L1
+            // now, a whole iteration ahead (this wait is short when the epilogue is the slower stage)
+            if (it + 1 < niter)
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(P.skip + offs[u] + (size_t)2 * P.Hout * P.Wout * 8));
           } else {
             sk[u][0] = sk[u][1] = make_uint4(0, 0, 0, 0);
           }
