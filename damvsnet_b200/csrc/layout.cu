@@ -9,24 +9,47 @@
 namespace damvs {
 
 constexpr int kTilePix = 128;
+constexpr int kTilePitch = kTilePix + 4;  // keeps rows 16-byte aligned for float4 stores
 
-// in [B][C][HW] -> out [B][HW][C]
-__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                           int C, long long HW) {
-  extern __shared__ float tile[];  // [C][kTilePix+1]
+// in [B][C][HW] -> out [B][HW][C].  A CTA of 128 threads walks 128-pixel tiles: float4 loads along the pixel
+// axis into a [C][128+4] tile (conflict free), then every thread writes one pixel's C channels as float4s.
+__global__ void __launch_bounds__(128) nchw_to_nhwc_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                           int C, long long HW, int tiles_per_cta) {
+  extern __shared__ __align__(16) float tile[];  // [C][kTilePitch]
   const int b = blockIdx.y;
-  const long long p0 = (long long)blockIdx.x * kTilePix;
-  const int np = (int)min((long long)kTilePix, HW - p0);
-  const float* src = in + (long long)b * C * HW + p0;
-  for (int i = threadIdx.x; i < C * kTilePix; i += blockDim.x) {
-    int c = i / kTilePix, p = i - c * kTilePix;
-    if (p < np) tile[c * (kTilePix + 1) + p] = __ldcs(src + (long long)c * HW + p);
-  }
-  __syncthreads();
-  float* dst = out + ((long long)b * HW + p0) * C;
-  for (int i = threadIdx.x; i < np * C; i += blockDim.x) {
-    int p = i / C, c = i - p * C;
-    dst[i] = tile[c * (kTilePix + 1) + p];
+  const int t = threadIdx.x;
+  const bool vec = (HW % 4 == 0);
+  for (int it = 0; it < tiles_per_cta; ++it) {
+    const long long p0 = ((long long)blockIdx.x * tiles_per_cta + it) * kTilePix;
+    if (p0 >= HW) break;
+    const int np = (int)min((long long)kTilePix, HW - p0);
+    const float* src = in + (long long)b * C * HW + p0;
+    if (vec) {
+      for (int i = t; i < C * (kTilePix / 4); i += blockDim.x) {
+        const int c = i / (kTilePix / 4), p4 = (i - c * (kTilePix / 4)) * 4;
+        if (p4 < np) {
+          const float4 v = __ldcs(reinterpret_cast<const float4*>(src + (long long)c * HW + p4));
+          *reinterpret_cast<float4*>(tile + c * kTilePitch + p4) = v;
+        }
+      }
+    } else {
+      for (int i = t; i < C * kTilePix; i += blockDim.x) {
+        const int c = i / kTilePix, p = i - c * kTilePix;
+        if (p < np) tile[c * kTilePitch + p] = __ldcs(src + (long long)c * HW + p);
+      }
+    }
+    __syncthreads();
+    if (t < np) {
+      float* dst = out + ((long long)b * HW + p0 + t) * C;
+      if (C % 4 == 0) {
+        for (int c = 0; c < C; c += 4)
+          *reinterpret_cast<float4*>(dst + c) = make_float4(tile[c * kTilePitch + t], tile[(c + 1) * kTilePitch + t],
+                                                            tile[(c + 2) * kTilePitch + t], tile[(c + 3) * kTilePitch + t]);
+      } else {
+        for (int c = 0; c < C; ++c) dst[c] = tile[c * kTilePitch + t];
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -80,11 +103,14 @@ extern "C" int damvs_nchw_to_nhwc_f32(const float* in, float* out, int B, int C,
   DAMVS_REQUIRE(in && out, "nchw_to_nhwc: null pointer");
   DAMVS_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && C <= 256, "nchw_to_nhwc: bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
   long long HW = (long long)H * W;
-  dim3 grid((unsigned)((HW + kTilePix - 1) / kTilePix), B);
-  size_t smem = (size_t)C * (kTilePix + 1) * sizeof(float);
+  const long long tiles = (HW + kTilePix - 1) / kTilePix;
+  const int tiles_per_cta = tiles >= 4 * 148 * 8 ? 4 : 1;
+  dim3 grid((unsigned)((tiles + tiles_per_cta - 1) / tiles_per_cta), B);
+  size_t smem = (size_t)C * kTilePitch * sizeof(float);
+  DAMVS_REQUIRE(aligned16(in) && aligned16(out), "nchw_to_nhwc: pointers must be 16-byte aligned");
   if (smem > 48 * 1024)
     DAMVS_CUDA_OK(cudaFuncSetAttribute(nchw_to_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  nchw_to_nhwc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in, out, C, HW);
+  nchw_to_nhwc_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(in, out, C, HW, tiles_per_cta);
   DAMVS_LAUNCH_OK("nchw_to_nhwc");
   return DAMVS_OK;
 }
