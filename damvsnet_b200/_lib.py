@@ -41,6 +41,11 @@ _SIGNATURES = {
     "damvs_softmax_regress_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                           c_int, c_int, c_int, c_void_p]),
     "damvs_depth_regression_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "damvs_softmax_regress_bwd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_void_p]),
+    "damvs_conv3d_bwd_pre": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_void_p]),
+    "damvs_conv3d_wgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "damvs_warp_agg_bwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                   POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "damvs_launch_count": (c_uint64, []),
 }
 

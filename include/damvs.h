@@ -132,6 +132,40 @@ int damvs_softmax_regress_fwd(const float* logits, const float* depth_hyp, float
 int damvs_depth_regression_fwd(const float* prob, const float* depth_hyp, float* out, int B, int D, int H,
                                int W, int per_pixel_hyp, void* stream);
 
+/* ---- backward (training with BatchNorm statistics held fixed) ---------------- */
+/* The reference's backward is PyTorch autograd; these are the native counterparts for the hot path.
+ * Data gradients of a conv block are one more damvs_conv3d_fwd call with re-packed weights (the adjoint of a
+ * stride-1 conv is a stride-1 conv with transposed + flipped weights, of a stride-2 conv the transposed
+ * conv, and vice versa) -- see damvsnet_b200/autograd.py.                                              */
+
+/* Gradient of the head (models/cas_mvsnet.py:105-124) w.r.t. the logits:
+ *   g_logit[k] = p_k (g_p[k] - sum_j p_j g_p[j]),  g_p[k] = g_depth d_k + g_var 3/(2 sqrt S) (d_k - depth)^2 + g_prob[k]
+ * g_depth, g_var, g_prob: incoming gradients, any may be NULL (= zero).  g_hyp (optional, per-pixel hypotheses
+ * only) receives d/d depth_values for grad_method "undetach".  photometric_confidence has no gradient
+ * (computed under no_grad in the reference, cas_mvsnet.py:113).                                           */
+int damvs_softmax_regress_bwd(const float* prob, const float* depth_hyp, const float* depth, const float* g_depth,
+                              const float* g_var, const float* g_prob, float* g_logits, float* g_hyp, int B, int D,
+                              int H, int W, int per_pixel_hyp, void* stream);
+
+/* For out = skip + act(y * scale + shift) (one conv block): g_y = g_out * [act active] * scale, written as a G8
+ * volume of `dtype`, and sums[c] = {sum g_z, sum g_z * y} (fp32 [C][2], ACCUMULATED: zero it first; NULL to
+ * skip), from which d(scale) and d(shift) -- hence d(gamma), d(beta) -- follow.  g_skip is g_out itself.   */
+int damvs_conv3d_bwd_pre(const void* g_out, const void* out, const void* skip, const float* scale, const float* shift,
+                         void* g_y, float* sums, int dtype, int B, int C, int D, int H, int W, int relu, void* stream);
+
+/* Weight gradient of a conv block in PyTorch layout (Conv3d [Cout,Cin,3,3,3], ConvTranspose3d [Cin,Cout,3,3,3]),
+ * fp32, overwritten.  desc describes the FORWARD convolution; in_dtype / out_dtype are the dtypes of x and g_y. */
+int damvs_conv3d_wgrad(const damvs_conv3d_desc* desc, const void* x, const void* g_y, float* dw, void* stream);
+
+/* Backward of damvs_warp_agg_fwd: g_vol (G8, g_dtype) -> g_ref [B,H,W,C] (overwritten), g_src[v] [B,H,W,C]
+ * (ACCUMULATED with vector atomics: zero them first; HOST array of device pointers), g_wnet [C+5] gradients
+ * of the folded view-weight parameters in the layout of `wnet` (ACCUMULATED; NULL to skip; adaptive only).
+ * The sampling grid and the hypotheses receive no gradient, as in the reference (models/module.py:307).   */
+int damvs_warp_agg_bwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
+                       const float* depth_hyp, const float* wnet, const void* g_vol, int g_dtype, float* g_ref,
+                       float* const* g_src, float* g_wnet, int B, int C, int D, int H, int W, int mode,
+                       int per_pixel_hyp, void* stream);
+
 /* Number of kernel launches this library has issued in this process (for bench.py's gpu_launches). */
 uint64_t damvs_launch_count(void);
 
