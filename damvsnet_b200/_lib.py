@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_size_t, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_C", "libdamvs_b200.so")
@@ -42,10 +42,21 @@ _SIGNATURES = {
                                           c_int, c_int, c_int, c_void_p]),
     "damvs_depth_regression_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "damvs_softmax_regress_bwd": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_void_p]),
-    "damvs_conv3d_bwd_pre": (c_int, [c_void_p] * 7 + [c_int] * 7 + [c_void_p]),
+    "damvs_bn_stats": (c_int, [c_void_p] + [c_int] * 6 + [c_void_p, c_void_p]),
+    "damvs_bn_apply": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+    "damvs_bn_bwd": (c_int, [c_void_p] * 9 + [c_int] * 7 + [c_void_p]),
+    "damvs_plain_to_g8": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "damvs_conv3d_wgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
     "damvs_warp_agg_bwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
                                    POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "damvs_warp_score_fwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6
+                             + [c_void_p]),
+    "damvs_warp_weighted_fwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p]
+                                + [c_int] * 7 + [c_void_p]),
+    "damvs_warp_score_bwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     POINTER(c_void_p), c_void_p] + [c_int] * 6 + [c_void_p]),
+    "damvs_warp_weighted_bwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                        c_void_p, POINTER(c_void_p), c_void_p] + [c_int] * 6 + [c_void_p]),
     "damvs_launch_count": (c_uint64, []),
 }
 

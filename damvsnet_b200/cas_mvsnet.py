@@ -11,6 +11,7 @@ from typing import Dict, List, Optional
 import torch
 import torch.nn as nn
 
+from . import autograd as ag
 from . import ops
 from .module import AggWeightNetVolume, CostRegNet
 
@@ -40,10 +41,26 @@ class DepthNet(nn.Module):
                     depth_values: torch.Tensor, out_dtype: Optional[torch.dtype] = None) -> ops.G8Volume:
         """Aggregated cost volume (reference models/cas_mvsnet.py:30-87) as a G8 volume."""
         rot_trans = self.stage_rot_trans(proj_matrices)
+        out_dtype = out_dtype or ops.volume_dtype()
+        wn = self.weight_net[stage_idx] if self.mode == "adaptive" else None
+        batch_stats = wn is not None and wn.training
+        params = tuple(wn.w_net.parameters()) if wn is not None else ()
+        if batch_stats or ag.wants_grad(*features, *params):
+            # training path: same kernels' worth of work, recorded on the autograd tape (damvsnet_b200/autograd.py)
+            with torch.no_grad():
+                rot_trans = rot_trans.detach()          # the sampling grid is not differentiated (module.py:307)
+                dv = depth_values.detach().contiguous()
+            nhwc = [ag.NhwcFn.apply(f) for f in features]
+            if batch_stats:
+                w1 = wn.w_net[0].conv.weight.reshape(-1)
+                s_vol = ag.WarpScoreFn.apply(w1, rot_trans, dv, *nhwc)
+                wt_vol = wn.score_to_weight(s_vol)
+                return ops.G8Volume(ag.WarpWeightedFn.apply(wt_vol, rot_trans, dv, out_dtype, *nhwc))
+            wnet = wn.folded_with_grad() if wn is not None else None
+            return ops.G8Volume(ag.WarpAggFn.apply(wnet, rot_trans, dv, self.mode, out_dtype, *nhwc))
         nhwc = [ops.features_to_nhwc(f) for f in features]
-        wnet = self.weight_net[stage_idx].folded() if self.mode == "adaptive" else None
-        return ops.warp_aggregate(nhwc[0], nhwc[1:], rot_trans, depth_values, wnet, self.mode,
-                                  out_dtype or ops.volume_dtype())
+        wnet = wn.folded() if wn is not None else None
+        return ops.warp_aggregate(nhwc[0], nhwc[1:], rot_trans, depth_values, wnet, self.mode, out_dtype)
 
     def forward(self, stage_idx, features, proj_matrices, depth_values, num_depth, cost_regularization,
                 prob_volume_init=None) -> Dict[str, torch.Tensor]:
@@ -60,6 +77,9 @@ class DepthNet(nn.Module):
         if dv.dim() == 2:
             b, _, h, w = logits.shape
             dv = dv.view(b, -1, 1, 1).expand(-1, -1, h, w).contiguous()
-        prob, depth, conf, var = ops.softmax_regress(logits, dv)
+        if ag.wants_grad(logits, dv):
+            prob, depth, conf, var = ag.HeadFn.apply(logits, dv)
+        else:
+            prob, depth, conf, var = ops.softmax_regress(logits, dv)
         return {"depth": depth, "photometric_confidence": conf, "variance": var,
                 "prob_volume": prob, "depth_values": depth_values}

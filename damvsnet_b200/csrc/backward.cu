@@ -1,12 +1,11 @@
-// Backward kernels of the hot path (training with BatchNorm statistics held fixed).
+// Backward kernels of the hot path: regression head and convolution weight gradients.
 //
 // The reference's backward is PyTorch autograd through softmax / regression, nn.Conv3d /
 // nn.ConvTranspose3d / BatchNorm3d (reference models/module.py:117-202, 510-541) and the hypothesis
 // variance (models/cas_mvsnet.py:105-124).  Here:
 //   * head_bwd_kernel        closed-form gradient of depth / variance / prob_volume w.r.t. the logits
 //                            (and optionally the hypotheses), SURVEY.md section 3.2;
-//   * conv_bwd_pre_kernel    for out = skip + relu(y*scale + shift): g_y = g_out * [relu active] * scale and
-//                            the per-channel sums that give d(scale), d(shift);
+//   * (BatchNorm + ReLU backward lives in bn.cu)
 //   * conv_wgrad_kernel      dW[co][ci][tap] = sum_voxels g_y[co](o) * x[ci](i(o, tap)) (CUDA cores, fp32 atomics).
 // The data gradient of a conv block is one more forward-type convolution (transposed roles), run by the
 // existing conv kernels with re-packed weights -- see damvsnet_b200/autograd.py.
@@ -54,62 +53,6 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const float* __restrict__
     const float g = gd * dk + cv * t * t + (gp ? __ldg(gp + (long long)k * HW) : 0.f);
     gl[(long long)k * HW] = pk * (g - dot);
     if (gh) gh[(long long)k * HW] = gd * pk + 2.f * cv * pk * t;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// out = skip + act(y * scale + shift).  One thread per (voxel, 8-channel group).
-template <typename T>
-__global__ void __launch_bounds__(256) conv_bwd_pre_kernel(const T* __restrict__ g_out, const T* __restrict__ out,
-                                                           const T* __restrict__ skip, const float* __restrict__ scale,
-                                                           const float* __restrict__ shift, T* __restrict__ g_y,
-                                                           float* __restrict__ sums /* [C][2]: sum g_z, sum g_z*y */,
-                                                           int G, long long V, int relu) {
-  __shared__ float s_sum[16][8][2];  // per warp
-  const int bg = blockIdx.y, g = bg % G;
-  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  float gz[8], gzy[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) gz[j] = gzy[j] = 0.f;
-  if (v < V) {
-    const size_t off = ((size_t)bg * V + v) * 8;
-    F8 go = load8(g_out + off), o = load8(out + off), r;
-    if (skip) {
-      F8 sk = load8(skip + off);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[j] -= sk.v[j];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = g * 8 + j;
-      const float sc = scale ? __ldg(scale + c) : 1.f, sh = shift ? __ldg(shift + c) : 0.f;
-      const bool on = !relu || o.v[j] > 0.f;
-      const float z = on ? go.v[j] : 0.f;
-      gz[j] = z;
-      gzy[j] = (on && sc != 0.f) ? z * (o.v[j] - sh) / sc : 0.f;  // y = (act - shift) / scale where the ReLU is active
-      r.v[j] = z * sc;
-    }
-    store8(g_y + off, r);
-  }
-  if (sums) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float a = gz[j], b2 = gzy[j];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        a += __shfl_xor_sync(0xffffffffu, a, o);
-        b2 += __shfl_xor_sync(0xffffffffu, b2, o);
-      }
-      if (lane == 0) { s_sum[warp][j][0] = a; s_sum[warp][j][1] = b2; }
-    }
-    __syncthreads();
-    if (threadIdx.x < 16) {
-      const int j = threadIdx.x >> 1, w = threadIdx.x & 1;
-      float a = 0.f;
-      for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a += s_sum[k][j][w];
-      atomicAdd(sums + (g * 8 + j) * 2 + w, a);
-    }
   }
 }
 
@@ -192,28 +135,6 @@ extern "C" int damvs_softmax_regress_bwd(const float* prob, const float* depth_h
   head_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(prob, depth_hyp, depth, g_depth, g_var, g_prob,
                                                                                       g_logits, g_hyp, D, HW, total, per_pixel_hyp);
   DAMVS_LAUNCH_OK("head_bwd kernel");
-  return DAMVS_OK;
-}
-
-extern "C" int damvs_conv3d_bwd_pre(const void* g_out, const void* out, const void* skip, const float* scale, const float* shift,
-                                    void* g_y, float* sums, int dtype, int B, int C, int D, int H, int W, int relu, void* stream) {
-  DAMVS_REQUIRE(g_out && out && g_y, "conv3d_bwd_pre: null pointer");
-  DAMVS_REQUIRE(B > 0 && C > 0 && C % 8 == 0 && D > 0 && H > 0 && W > 0, "conv3d_bwd_pre: bad shape");
-  DAMVS_REQUIRE(aligned16(g_out) && aligned16(out) && aligned16(g_y) && aligned16(skip), "conv3d_bwd_pre: pointers must be 16-byte aligned");
-  const long long V = (long long)D * H * W;
-  const int G = C / 8;
-  DAMVS_REQUIRE((long long)B * G <= 65535, "conv3d_bwd_pre: B*C/8 too large");
-  dim3 grid((unsigned)((V + 255) / 256), B * G);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == DAMVS_F32)
-    conv_bwd_pre_kernel<float><<<grid, 256, 0, st>>>((const float*)g_out, (const float*)out, (const float*)skip, scale, shift,
-                                                    (float*)g_y, sums, G, V, relu);
-  else if (dtype == DAMVS_BF16)
-    conv_bwd_pre_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)g_out, (const __nv_bfloat16*)out,
-                                                            (const __nv_bfloat16*)skip, scale, shift, (__nv_bfloat16*)g_y, sums, G, V, relu);
-  else
-    return set_error(DAMVS_ERR_INVALID, "conv3d_bwd_pre: bad dtype %d", dtype);
-  DAMVS_LAUNCH_OK("conv_bwd_pre kernel");
   return DAMVS_OK;
 }
 

@@ -804,6 +804,7 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
     GO(MODE_S1, 16, 2, 2); GO(MODE_S1, 16, 1, 2);   // conv0 (stage 2), conv2
     GO(MODE_S1, 16, 2, 4); GO(MODE_S1, 16, 1, 4);   // conv0 (stage 1)
     GO(MODE_S1, 32, 1, 4);                           // conv4
+    GO(MODE_S1, 32, 1, 1);                           // adjoint of conv0 (stage 1): 8 -> 32
     GO(MODE_S1, 32, 1, 8);                           // conv6 (two output halves)
     GO(MODE_S2, 16, 2, 1); GO(MODE_S2, 16, 1, 1);   // conv1
     GO(MODE_S2, 32, 1, 2);                           // conv3

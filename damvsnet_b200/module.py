@@ -8,9 +8,10 @@ behind include/damvs.h; parameters stay ordinary fp32 ``nn.Parameter``s in
 PyTorch layout and are repacked (BatchNorm folded, weights reordered / cast)
 into a per-module cache keyed on the parameters' version counters.
 
-Inference (``eval()``) is the native path.  Training-mode BatchNorm (batch
-statistics) is not implemented natively yet: modules raise in train mode rather
-than silently computing something else.
+Inference (``eval()`` under ``no_grad``) runs the fused kernels (BatchNorm folded into the
+convolution epilogue).  With gradients enabled, or in ``train()`` mode (batch statistics),
+the blocks run through ``damvsnet_b200.autograd``: raw convolution -> statistics ->
+normalise/ReLU/skip, with native backward kernels.
 """
 from __future__ import annotations
 
@@ -19,6 +20,7 @@ from typing import Dict, Optional, Tuple
 import torch
 import torch.nn as nn
 
+from . import autograd as ag
 from . import ops
 from .ops import G8Volume
 
@@ -44,10 +46,34 @@ class _ConvBlock(nn.Module):
     def _init_cache(self):
         self._packed: Dict[tuple, tuple] = {}
 
-    def _train_guard(self):
-        if self.training and self.bn is not None:
-            raise NotImplementedError(
-                "damvsnet_b200: training-mode BatchNorm (batch statistics) has no native kernel yet; call .eval()")
+    def _cached(self, key, ver, make):
+        hit = self._packed.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        val = make()
+        self._packed[key] = (ver, val)
+        return val
+
+    def packed_weight(self, impl: int) -> torch.Tensor:
+        """Packed convolution weights alone (no BatchNorm fold): the training path applies BatchNorm separately."""
+        w = self.conv.weight
+        return self._cached(("w", impl, w.device), _versions(w), lambda: ops.conv3d_pack_weight(
+            w.detach().float(), self.in_channels, self.out_channels, self.transposed, impl, self.stride))
+
+    def packed_adjoint(self, impl: int) -> torch.Tensor:
+        """Packed weights of the adjoint convolution (data gradient).  Stride-1: transposed + flipped weights;
+        stride-2 conv <-> transposed conv share the weight tensor as it is."""
+        w = self.conv.weight
+        cin, cout = self.in_channels, self.out_channels
+
+        def make():
+            wd = w.detach().float()
+            if self.transposed:          # adjoint: Conv3d(cout -> cin, stride 2), weight [cin, cout, ...] as is
+                return ops.conv3d_pack_weight(wd.contiguous(), cout, cin, False, impl, 2)
+            if self.stride == 2:         # adjoint: ConvTranspose3d(cout -> cin), weight [cout, cin, ...] as is
+                return ops.conv3d_pack_weight(wd.contiguous(), cout, cin, True, impl, 2)
+            return ops.conv3d_pack_weight(wd.transpose(0, 1).flip(2, 3, 4).contiguous(), cout, cin, False, impl, 1)
+        return self._cached(("adj", impl, w.device), _versions(w), make)
 
     def prepared(self, impl: int):
         """(packed weight, scale, shift) for `impl` on the parameters' device, rebuilt when they change."""
@@ -73,9 +99,17 @@ class _ConvBlock(nn.Module):
 
     def forward_g8(self, vol: G8Volume, skip: Optional[G8Volume] = None, out_dtype: Optional[torch.dtype] = None) -> G8Volume:
         """out = skip + relu(bn(conv(vol))) on G8 volumes (the path CostRegNet uses)."""
-        self._train_guard()
         if self.kernel_size != 3:
             raise NotImplementedError("native conv blocks are 3x3x3 only")
+        bn = self.bn
+        batch_stats = bn is not None and (self.training or not bn.track_running_stats)
+        params = (self.conv.weight,) + ((bn.weight, bn.bias) if bn is not None else ())
+        if batch_stats or ag.wants_grad(vol.data, None if skip is None else skip.data, *params):
+            if out_dtype is not None and out_dtype != vol.dtype:
+                raise NotImplementedError("training path keeps one volume dtype")
+            out = ag.ConvBlockFn.apply(vol.data, None if skip is None else skip.data, self.conv.weight,
+                                       None if bn is None else bn.weight, None if bn is None else bn.bias, self)
+            return G8Volume(out)
         impl = ops.conv_impl_for(self.in_channels, self.out_channels, self.stride, self.transposed)
         packed, scale, shift = self.prepared(impl)
         return ops.conv3d(vol, packed, scale, shift, self.out_channels, self.stride, self.transposed, self.relu, skip,
@@ -162,6 +196,21 @@ class CostRegNet(nn.Module):
         self._prob_packed[key] = (ver, packed)
         return packed
 
+    def _prob_adjoint(self, impl: int) -> torch.Tensor:
+        """Packed weights of the adjoint of `prob`: Conv3d(8 (zero-padded from 1) -> base_channels)."""
+        w = self.prob.weight
+        key = ("adj", impl, w.device)
+        ver = _versions(w)
+        hit = self._prob_packed.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        wd = w.detach().float()                                              # [1, C, 3,3,3]
+        padded = torch.zeros((8,) + tuple(wd.shape[1:]), dtype=torch.float32, device=w.device)
+        padded[:1] = wd
+        packed = ops.conv3d_pack_weight(padded.transpose(0, 1).flip(2, 3, 4).contiguous(), 8, self.base_channels, False, impl)
+        self._prob_packed[key] = (ver, packed)
+        return packed
+
     def forward_g8(self, vol: G8Volume) -> torch.Tensor:
         """G8 cost volume -> logits [B,D,H,W] fp32 (the squeeze(1) of the reference output)."""
         b, c, d, h, w = vol.shape
@@ -176,6 +225,8 @@ class CostRegNet(nn.Module):
         x = self.conv7.forward_g8(x, skip=conv4)     # conv4 + conv7(x)
         x = self.conv9.forward_g8(x, skip=conv2)
         x = self.conv11.forward_g8(x, skip=conv0)
+        if ag.wants_grad(x.data, self.prob.weight):
+            return ag.ProbConvFn.apply(x.data, self.prob.weight, self)
         impl = ops.conv_impl_for(self.base_channels, 1, 1, False)
         return ops.conv3d(x, self._prob_prepared(impl), None, None, 1, 1, False, False, None, torch.float32, True, impl)
 
@@ -207,8 +258,7 @@ class AggWeightNetVolume(nn.Module):
         """[C+5] fp32: w1[C], scale1, shift1, w2, scale2, shift2 (include/damvs.h, damvs_warp_agg_fwd)."""
         a, b = self.w_net[0], self.w_net[1]
         if self.training:
-            raise NotImplementedError(
-                "damvsnet_b200: training-mode view-weight BatchNorm has no native kernel yet; call .eval()")
+            raise RuntimeError("folded() is the eval-mode form; in training DepthNet uses score -> chain -> weighted")
         tensors = (a.conv.weight, a.bn.weight, a.bn.bias, a.bn.running_mean, a.bn.running_var,
                    b.conv.weight, b.bn.weight, b.bn.bias, b.bn.running_mean, b.bn.running_var)
         ver = _versions(*tensors)
@@ -222,6 +272,33 @@ class AggWeightNetVolume(nn.Module):
                          b.conv.weight.detach().float().reshape(-1), s2, b2]).contiguous()
         self._folded[dev] = (ver, vec)
         return vec
+
+    def folded_with_grad(self) -> torch.Tensor:
+        """folded() as a differentiable function of the parameters (eval-mode BatchNorm, gradients enabled):
+        the kernel's gradient w.r.t. the C+5 vector flows back to conv weights, gamma and beta through autograd."""
+        a, b = self.w_net[0], self.w_net[1]
+
+        def affine(bn):
+            scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            return scale, bn.bias - bn.running_mean * scale
+        s1, b1 = affine(a.bn)
+        s2, b2 = affine(b.bn)
+        return torch.cat([a.conv.weight.reshape(-1), s1, b1, b.conv.weight.reshape(-1), s2, b2]).float().contiguous()
+
+    def score_to_weight(self, s_vol: torch.Tensor) -> torch.Tensor:
+        """Training-mode tail of the net on per-view score volumes [n_src,B,D,H,W] -> weights, same shape.
+        s_v is the output of w_net[0].conv; what follows is BatchNorm3d(1) -> ReLU -> 1x1x1 conv (a scalar) ->
+        BatchNorm3d(1) -> ReLU, called once per source view exactly as models/cas_mvsnet.py:71 does, so the
+        batch statistics and the running-buffer updates are per view.  These are scalar volumes (1/C of the
+        cost volume); the nn.BatchNorm3d modules themselves run them."""
+        a, b = self.w_net[0], self.w_net[1]
+        out = []
+        for v in range(s_vol.shape[0]):
+            x = s_vol[v].unsqueeze(1)
+            x = torch.relu(a.bn(x))
+            x = torch.relu(b.bn(x * b.conv.weight.reshape(())))
+            out.append(x.squeeze(1))
+        return torch.stack(out, 0)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """Stand-alone reference signature [B,C,D,H,W] -> [B,1,D,H,W].  Not used by DepthNet (fused there);

@@ -74,7 +74,7 @@ def tc_supported(cin: int, cout: int, stride: int, transposed: bool) -> bool:
         return (g, cp(cout)) in ((1, 16), (2, 32), (4, 64))
     if cin == 64 and cout == 64:
         return True                      # two launches of 32 output channels
-    return (g, cp(cout)) in ((1, 16), (2, 16), (4, 16), (4, 32), (8, 32))
+    return (g, cp(cout)) in ((1, 16), (2, 16), (4, 16), (4, 32), (8, 32), (1, 32))
 
 
 # --------------------------------------------------------------------------

@@ -132,7 +132,7 @@ int damvs_softmax_regress_fwd(const float* logits, const float* depth_hyp, float
 int damvs_depth_regression_fwd(const float* prob, const float* depth_hyp, float* out, int B, int D, int H,
                                int W, int per_pixel_hyp, void* stream);
 
-/* ---- backward (training with BatchNorm statistics held fixed) ---------------- */
+/* ---- backward ----------------------------------------------------------------- */
 /* The reference's backward is PyTorch autograd; these are the native counterparts for the hot path.
  * Data gradients of a conv block are one more damvs_conv3d_fwd call with re-packed weights (the adjoint of a
  * stride-1 conv is a stride-1 conv with transposed + flipped weights, of a stride-2 conv the transposed
@@ -147,11 +147,30 @@ int damvs_softmax_regress_bwd(const float* prob, const float* depth_hyp, const f
                               const float* g_var, const float* g_prob, float* g_logits, float* g_hyp, int B, int D,
                               int H, int W, int per_pixel_hyp, void* stream);
 
-/* For out = skip + act(y * scale + shift) (one conv block): g_y = g_out * [act active] * scale, written as a G8
- * volume of `dtype`, and sums[c] = {sum g_z, sum g_z * y} (fp32 [C][2], ACCUMULATED: zero it first; NULL to
- * skip), from which d(scale) and d(shift) -- hence d(gamma), d(beta) -- follow.  g_skip is g_out itself.   */
-int damvs_conv3d_bwd_pre(const void* g_out, const void* out, const void* skip, const float* scale, const float* shift,
-                         void* g_y, float* sums, int dtype, int B, int C, int D, int H, int W, int relu, void* stream);
+/* ---- training-mode BatchNorm3d around the conv blocks (models/module.py:141-159, 184-202) ---------------
+ * In training the conv kernels write the raw convolution y (damvs_conv3d_fwd with scale = shift = skip = NULL,
+ * relu = 0); these three streaming kernels do the rest on G8 volumes of `dtype`.  The C-sized coefficient
+ * algebra (statistics -> scale/shift, BatchNorm backward -> k1,k2,k3, running buffers) is the caller's.   */
+
+/* sums[c] += {sum y, sum y^2} over (B,D,H,W); sums is fp64 [C][2], ACCUMULATED (zero it first). */
+int damvs_bn_stats(const void* y, int dtype, int B, int C, int D, int H, int W, double* sums, void* stream);
+
+/* out = skip + act(y * scale[c] + shift[c]); skip may be NULL; out may alias y. */
+int damvs_bn_apply(const void* y, const float* scale, const float* shift, const void* skip, void* out, int dtype, int B,
+                   int C, int D, int H, int W, int relu, void* stream);
+
+/* Backward of damvs_bn_apply.  g_z = g_out * [act active] with the activation recomputed from y, scale, shift;
+ *   sums[c] += {sum g_z, sum g_z * y}   (fp64 [C][2], ACCUMULATED; NULL to skip)
+ *   g_y = k1[c] * g_z + k2[c] * y + k3[c]  (NULL k1 = 1, NULL k2/k3 = 0; g_y NULL to skip)
+ * Batch statistics need two calls (sums, then g_y with the BatchNorm-backward coefficients); fixed statistics
+ * one call with k1 = scale.  The gradient of the skip input is g_out itself.                              */
+int damvs_bn_bwd(const void* g_out, const void* y, const float* scale, const float* shift, const float* k1, const float* k2,
+                 const float* k3, void* g_y, double* sums, int dtype, int B, int C, int D, int H, int W, int relu,
+                 void* stream);
+
+/* [voxels] fp32 -> G8 volume of one channel group: channel 0 = value, channels 1..7 = 0 (gradient of the
+ * single-channel `prob` convolution's output, fed to the adjoint convolution and to damvs_conv3d_wgrad). */
+int damvs_plain_to_g8(const float* in, void* out, int dtype, long long voxels, void* stream);
 
 /* Weight gradient of a conv block in PyTorch layout (Conv3d [Cout,Cin,3,3,3], ConvTranspose3d [Cin,Cout,3,3,3]),
  * fp32, overwritten.  desc describes the FORWARD convolution; in_dtype / out_dtype are the dtypes of x and g_y. */
@@ -165,6 +184,25 @@ int damvs_warp_agg_bwd(const float* ref_nhwc, const float* const* src_nhwc, int 
                        const float* depth_hyp, const float* wnet, const void* g_vol, int g_dtype, float* g_ref,
                        float* const* g_src, float* g_wnet, int B, int C, int D, int H, int W, int mode,
                        int per_pixel_hyp, void* stream);
+
+/* ---- warp + aggregation with the view-weight net in training mode (batch statistics) --------------------
+ * AggWeightNetVolume's BatchNorms (models/module.py:548-551) then normalise over a whole per-view score volume,
+ * so the adaptive aggregation splits into  s_v = sum_c w1[c] (ref - warp_v)[c]^2  ("score"),  the scalar
+ * chain s_v -> wt_v on [n_src][B][D][H][W] fp32 volumes (caller), and
+ * vol = sum_v (wt_v + 1)(ref - warp_v)^2 / n_src ("weighted").  g_ref / g_src / g_w1 are ACCUMULATED.      */
+int damvs_warp_score_fwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
+                         const float* depth_hyp, const float* w1, float* s_vol, int B, int C, int D, int H, int W,
+                         int per_pixel_hyp, void* stream);
+int damvs_warp_weighted_fwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
+                            const float* depth_hyp, const float* wt_vol, void* out_vol, int B, int C, int D, int H, int W,
+                            int per_pixel_hyp, int out_dtype, void* stream);
+int damvs_warp_score_bwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
+                         const float* depth_hyp, const float* w1, const float* g_s_vol, float* g_ref, float* const* g_src,
+                         float* g_w1, int B, int C, int D, int H, int W, int per_pixel_hyp, void* stream);
+int damvs_warp_weighted_bwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
+                            const float* depth_hyp, const float* wt_vol, const void* g_vol, int g_dtype, float* g_ref,
+                            float* const* g_src, float* g_wt_vol, int B, int C, int D, int H, int W, int per_pixel_hyp,
+                            void* stream);
 
 /* Number of kernel launches this library has issued in this process (for bench.py's gpu_launches). */
 uint64_t damvs_launch_count(void);

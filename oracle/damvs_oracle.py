@@ -132,24 +132,34 @@ def bn_affine(sd: Dict[str, torch.Tensor], prefix: str):
     return scale, shift
 
 
-def view_weight(sq: torch.Tensor, sd: Dict[str, torch.Tensor], stage_idx: int) -> torch.Tensor:
-    """AggWeightNetVolume.forward in eval mode: [B,C,D,H,W] -> [B,1,D,H,W].
+def batch_norm(y: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, training: bool) -> torch.Tensor:
+    """nn.BatchNorm3d(momentum=0.1, eps=1e-5) (reference models/module.py:141,184).  Eval: the folded affine.
+    Training: normalise with the biased batch variance over (B,D,H,W); the running buffers are not touched
+    here (the oracle is functional; buffer updates are checked separately in the tests)."""
+    if training:
+        return F.batch_norm(y, None, None, sd[prefix + ".weight"], sd[prefix + ".bias"], True, 0.1, BN_EPS)
+    s, b = bn_affine(sd, prefix)
+    shape = (1, -1) + (1,) * (y.dim() - 2)
+    return y * s.view(shape) + b.view(shape)
+
+
+def view_weight(sq: torch.Tensor, sd: Dict[str, torch.Tensor], stage_idx: int, training: bool = False) -> torch.Tensor:
+    """AggWeightNetVolume.forward: [B,C,D,H,W] -> [B,1,D,H,W].
 
     Reference models/module.py:544-563: two 1x1x1 Conv3d(bias=False)+BN+ReLU
     blocks (``w_net``); ``conv0`` is constructed but never called.
     """
     p = f"DepthNet.weight_net.{stage_idx}.w_net."
     w1 = sd[p + "0.conv.weight"].view(1, -1, 1, 1, 1)
-    s1, b1 = bn_affine(sd, p + "0.bn")
     w2 = sd[p + "1.conv.weight"].view(())
-    s2, b2 = bn_affine(sd, p + "1.bn")
     s = (sq * w1).sum(dim=1, keepdim=True)
-    a = torch.relu(s * s1 + b1)
-    return torch.relu((a * w2) * s2 + b2)
+    a = torch.relu(batch_norm(s, sd, p + "0.bn", training))
+    return torch.relu(batch_norm(a * w2, sd, p + "1.bn", training))
 
 
 def aggregate(features: Sequence[torch.Tensor], proj_matrices: torch.Tensor, depth_values: torch.Tensor,
-              mode: str, sd: Optional[Dict[str, torch.Tensor]] = None, stage_idx: int = 0) -> torch.Tensor:
+              mode: str, sd: Optional[Dict[str, torch.Tensor]] = None, stage_idx: int = 0,
+              training: bool = False) -> torch.Tensor:
     """Multi-view cost volume [B,C,D,H,W].  Reference models/cas_mvsnet.py:19-87."""
     projs = torch.unbind(proj_matrices, 1)
     assert len(features) == len(projs)
@@ -171,7 +181,7 @@ def aggregate(features: Sequence[torch.Tensor], proj_matrices: torch.Tensor, dep
         for src, pm in zip(srcs, projs[1:]):
             wv = homo_warping(src, compose_projection(pm), ref_proj, depth_values)
             sq = (ref_vol - wv) ** 2                          # cas_mvsnet.py:66
-            wt = view_weight(sq, sd, stage_idx)               # cas_mvsnet.py:71
+            wt = view_weight(sq, sd, stage_idx, training)     # cas_mvsnet.py:71
             term = (wt + 1) * sq
             acc = term if acc is None else acc + term         # cas_mvsnet.py:73-76
         return acc / (n - 1)                                  # cas_mvsnet.py:87
@@ -181,30 +191,29 @@ def aggregate(features: Sequence[torch.Tensor], proj_matrices: torch.Tensor, dep
 # --------------------------------------------------------------------------
 # CostRegNet
 # --------------------------------------------------------------------------
-def conv_block(x, sd, prefix, stride=1):
-    """Conv3d(k3, padding=1, bias=False) + BN(eval) + ReLU.  Reference models/module.py:117-159."""
+def conv_block(x, sd, prefix, stride=1, training=False):
+    """Conv3d(k3, padding=1, bias=False) + BN + ReLU.  Reference models/module.py:117-159."""
     y = F.conv3d(x, sd[prefix + ".conv.weight"], None, stride=stride, padding=1)
-    s, b = bn_affine(sd, prefix + ".bn")
-    return torch.relu(y * s.view(1, -1, 1, 1, 1) + b.view(1, -1, 1, 1, 1))
+    return torch.relu(batch_norm(y, sd, prefix + ".bn", training))
 
 
-def deconv_block(x, sd, prefix):
-    """ConvTranspose3d(k3, s2, p1, op1, bias=False) + BN(eval) + ReLU.  Reference models/module.py:161-202."""
+def deconv_block(x, sd, prefix, training=False):
+    """ConvTranspose3d(k3, s2, p1, op1, bias=False) + BN + ReLU.  Reference models/module.py:161-202."""
     y = F.conv_transpose3d(x, sd[prefix + ".conv.weight"], None, stride=2, padding=1, output_padding=1)
-    s, b = bn_affine(sd, prefix + ".bn")
-    return torch.relu(y * s.view(1, -1, 1, 1, 1) + b.view(1, -1, 1, 1, 1))
+    return torch.relu(batch_norm(y, sd, prefix + ".bn", training))
 
 
-def cost_reg_net(x: torch.Tensor, sd: Dict[str, torch.Tensor], stage_idx: int) -> torch.Tensor:
+def cost_reg_net(x: torch.Tensor, sd: Dict[str, torch.Tensor], stage_idx: int, training: bool = False) -> torch.Tensor:
     """[B,C,D,H,W] -> logits [B,1,D,H,W].  Reference models/module.py:510-541."""
     p = f"cost_regularization.{stage_idx}."
-    c0 = conv_block(x, sd, p + "conv0")
-    c2 = conv_block(conv_block(c0, sd, p + "conv1", 2), sd, p + "conv2")
-    c4 = conv_block(conv_block(c2, sd, p + "conv3", 2), sd, p + "conv4")
-    y = conv_block(conv_block(c4, sd, p + "conv5", 2), sd, p + "conv6")
-    y = c4 + deconv_block(y, sd, p + "conv7")
-    y = c2 + deconv_block(y, sd, p + "conv9")
-    y = c0 + deconv_block(y, sd, p + "conv11")
+    t = training
+    c0 = conv_block(x, sd, p + "conv0", 1, t)
+    c2 = conv_block(conv_block(c0, sd, p + "conv1", 2, t), sd, p + "conv2", 1, t)
+    c4 = conv_block(conv_block(c2, sd, p + "conv3", 2, t), sd, p + "conv4", 1, t)
+    y = conv_block(conv_block(c4, sd, p + "conv5", 2, t), sd, p + "conv6", 1, t)
+    y = c4 + deconv_block(y, sd, p + "conv7", t)
+    y = c2 + deconv_block(y, sd, p + "conv9", t)
+    y = c0 + deconv_block(y, sd, p + "conv11", t)
     return F.conv3d(y, sd[p + "prob.weight"], None, stride=1, padding=1)
 
 
@@ -244,11 +253,13 @@ def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tenso
 # --------------------------------------------------------------------------
 def depthnet_forward(stage_idx: int, features: List[torch.Tensor], proj_matrices: torch.Tensor,
                      depth_values: torch.Tensor, sd: Dict[str, torch.Tensor], mode: str = "adaptive",
-                     return_volume: bool = False) -> Dict[str, torch.Tensor]:
-    """DepthNet.forward for one stage (reference models/cas_mvsnet.py:18-134), eval-mode BN."""
+                     return_volume: bool = False, training: bool = False) -> Dict[str, torch.Tensor]:
+    """DepthNet.forward for one stage (reference models/cas_mvsnet.py:18-134); `training` selects batch
+    statistics in every BatchNorm (model.train()).  Differentiable w.r.t. features and the tensors of `sd`
+    (torch CPU autograd), which is how the tests obtain reference gradients."""
     assert depth_values.dim() == 4
-    vol = aggregate(features, proj_matrices, depth_values, mode, sd, stage_idx)
-    logits = cost_reg_net(vol, sd, stage_idx).squeeze(1)
+    vol = aggregate(features, proj_matrices, depth_values, mode, sd, stage_idx, training)
+    logits = cost_reg_net(vol, sd, stage_idx, training).squeeze(1)
     out = regress_head(logits, depth_values)
     if return_volume:
         out["volume"] = vol

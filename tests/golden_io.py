@@ -38,3 +38,25 @@ def load_depthnet(mode: str):
 def load_homo():
     npz = np.load(os.path.join(GOLDEN, "homo_warping.npz"))
     return {k: torch.from_numpy(npz[k].astype(np.float32) if npz[k].dtype == np.float16 else npz[k]) for k in npz.files}
+
+
+def load_train_grads(mode: str, bn_mode: str):
+    """Training-path fixture (tests/golden/make_golden_train.py): inputs, weights, loss weights, the reference's
+    outputs, gradients and post-step BatchNorm buffers for mode in {adaptive, variance} x bn_mode in {train, eval}."""
+    npz = np.load(os.path.join(GOLDEN, "train_grads.npz"))
+    t = lambda a: torch.from_numpy(np.asarray(a))
+    tag = f"{mode}/{bn_mode}/"
+    out = {"features": list(t(npz["features"]).unbind(0)), "proj": t(npz["proj"]), "depth_values": t(npz["depth_values"]),
+           "r_depth": t(npz["r_depth"]), "r_prob": t(npz["r_prob"]), "r_var": t(npz["r_var"]),
+           "loss": float(npz[tag + "loss"]), "g_features": list(t(npz[tag + "g_features"]).unbind(0)),
+           "sd": {}, "grads": {}, "buffers": {}, "out": {}}
+    for k in npz.files:
+        if k.startswith(f"{mode}/w/"):
+            out["sd"][k[len(mode) + 3:]] = t(npz[k])
+        elif k.startswith(tag + "g/"):
+            out["grads"][k[len(tag) + 2:]] = t(npz[k])
+        elif k.startswith(tag + "buf/"):
+            out["buffers"][k[len(tag) + 4:]] = t(npz[k])
+        elif k.startswith(tag + "out/"):
+            out["out"][k[len(tag) + 4:]] = t(npz[k])
+    return out
