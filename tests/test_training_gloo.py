@@ -1,0 +1,82 @@
+"""World-size-2 gloo test of the data-parallel training plumbing (CPU only, no kernels): the flat gradient bucket
+averages per-rank gradients exactly like DistributedDataParallel would, skips frozen parameters, fills missing
+gradients with zeros, and the construction-time broadcast makes rank 1 equal to rank 0."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from damvsnet_b200 import training
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make_model(seed):
+    torch.manual_seed(seed)
+    m = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.BatchNorm1d(7), torch.nn.Linear(7, 3))
+    m[2].bias.requires_grad_(False)          # a frozen parameter stays out of the bucket
+    return m
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    model = _make_model(seed=rank)            # different init per rank ...
+    training.broadcast_module_state([model])  # ... until rank 0's state is broadcast
+    state = torch.cat([p.detach().flatten() for p in model.parameters()])
+    bucket = training.GradientBucket(model.parameters())
+    x = torch.full((4, 5), float(rank + 1))
+    model(x).sum().backward()
+    if rank == 1:
+        model[0].bias.grad = None              # a parameter without gradient on one rank counts as zero
+    local = [None if p.grad is None else p.grad.clone() for p in bucket.params]
+    finish = bucket.allreduce(async_op=True)
+    finish()
+    ret[rank] = (state, local, [p.grad.clone() for p in bucket.params], len(bucket.params), bucket.numel)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_bucket_allreduce_matches_mean_of_local_gradients():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        s0, l0, g0, n0, numel0 = ret[0]
+        s1, l1, g1, n1, _ = ret[1]
+    assert torch.equal(s0, s1), "broadcast_module_state did not synchronise the ranks"
+    assert n0 == n1 == 5 and numel0 == 5 * 7 + 7 + 7 + 7 + 7 * 3          # frozen bias excluded
+    for a, b, ga, gb in zip(l0, l1, g0, g1):
+        za = a if a is not None else torch.zeros_like(ga)
+        zb = b if b is not None else torch.zeros_like(ga)
+        want = (za + zb) / 2
+        torch.testing.assert_close(ga, want)
+        torch.testing.assert_close(gb, want)
+
+
+def test_bucket_is_noop_without_process_group():
+    m = _make_model(0)
+    m(torch.ones(4, 5)).sum().backward()
+    b = training.GradientBucket(m.parameters())
+    before = [p.grad.clone() for p in b.params]
+    assert b.allreduce() is None
+    for p, g in zip(b.params, before):
+        assert torch.equal(p.grad, g)
+
+
+def test_depth_loss_matches_reference_formula():
+    g = torch.Generator().manual_seed(0)
+    outs = [{"depth": torch.rand(2, 4, 6, generator=g) * 100} for _ in range(3)]
+    gts = [torch.rand(2, 4, 6, generator=g) * 100 for _ in range(3)]
+    masks = [(torch.rand(2, 4, 6, generator=g) > 0.3).float() for _ in range(3)]
+    got = training.depth_loss(outs, gts, masks, (0.5, 1.0, 2.0))
+    want = sum(w * torch.nn.functional.smooth_l1_loss(o["depth"][m > 0.5], t[m > 0.5]) for o, t, m, w in zip(outs, gts, masks, (0.5, 1.0, 2.0)))
+    torch.testing.assert_close(got, want)
