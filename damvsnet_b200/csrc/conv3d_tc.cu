@@ -46,7 +46,7 @@ namespace damvs {
 using namespace tc;
 
 constexpr int kP = 32;         // patch pitch in voxels (one TMA box row = 32 voxels * 16 B)
-constexpr int kMaxSlots = 8;   // depth-plane ring (actual depth chosen per launch)
+constexpr int kMaxSlots = 16;  // depth-plane ring (actual depth chosen per launch)
 constexpr int kMaxSteps = 96;
 constexpr uint32_t kMagic = 0x44544332u;  // "DTC2"
 
@@ -74,6 +74,7 @@ struct TcParams {
   int n0, Cout, relu, plain_out, niter, nsteps, nslots;
   int tiles_x, tiles_y, ntiles;  // persistent CTAs walk tiles blockIdx.x, blockIdx.x + gridDim.x, ...
   unsigned long long* trace;  // development aid: per-CTA event timestamps (null in production)
+  int dbg;                    // development aid (DAMVS_TC_DBG, trace builds only): bit0 skip epilogue body, bit1 skip MMA issue, bit2 skip loads
 };
 
 __host__ __device__ inline int steps_offset() { return (int)sizeof(PackedHeader); }
@@ -95,10 +96,18 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// Per-CTA event timestamps for DAMVS_TC_TRACE (development aid): compiled in only with -DDAMVS_TC_TRACE_BUILD, so the
+// production epilogue carries no timer reads, predicates or stores.
+#ifdef DAMVS_TC_TRACE_BUILD
 #define TRACE(slot_)                                                                                              \
   do {                                                                                                            \
     if (P.trace) P.trace[((size_t)blockIdx.x) * 64 + (slot_)] = gtime();                \
   } while (0)
+#define DBG(bit_) (P.dbg & (bit_))
+#else
+#define TRACE(slot_) do { } while (0)
+#define DBG(bit_) false
+#endif
 
 __device__ __forceinline__ float shfl_dn(uint32_t v, int d) { return __uint_as_float(__shfl_down_sync(0xffffffffu, v, d)); }
 
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
   const int ty0 = (((tile_) / P.tiles_x) % P.tiles_y) * TH;              \
   const int tx0 = ((tile_) % P.tiles_x) * G_::TW;
 
-  if (threadIdx.x == 0) TRACE(0);
+  if (threadIdx.x == 0) { TRACE(0); }
   // ---- one-time setup ------------------------------------------------------------------------
   {
     const uint4* wsrc = reinterpret_cast<const uint4*>(P.blob + weights_offset(nsteps));
@@ -258,7 +267,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int niter = P.niter;
-  if (threadIdx.x == 0) TRACE(1);
+  if (threadIdx.x == 0) { TRACE(1); }
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -270,6 +279,11 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
       TILE_COORDS(tile)
       for (int k = 0; k < nplanes; ++k) {
         if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+        if (DBG(4)) {   // development aid: no loads, the MMAs run on whatever the ring holds
+          mbar_arrive_expect_tx(&full[slot], 0);
+          if (++slot == nslots) { slot = 0; ++round; }
+          continue;
+        }
         mbar_arrive_expect_tx(&full[slot], bytes);
         uint8_t* dst = sA + slot * slot_stride;
         const int plane = k + G_::p0;
@@ -302,18 +316,18 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
         ++next_wait;
         if (++wait_slot == nslots) { wait_slot = 0; ++wait_round; }
       }
-      if (leader && acc_n < 12) TRACE(4 + acc_n);
+      if (leader && acc_n < 12) { TRACE(4 + acc_n); }
       const int buf = NBUF == 2 ? (acc_n & 1) : 0;
       if (acc_n >= NBUF) mbar_wait(&tmem_empty[buf], (NBUF == 2 ? ((acc_n >> 1) - 1) : (acc_n - 1)) & 1);
       tc_fence_after();
-      if (leader && acc_n < 12) TRACE(16 + acc_n);
+      if (leader && acc_n < 12) { TRACE(16 + acc_n); }
       const uint32_t dbase = tmem_base + buf * ACC_COLS;
       int s1 = base_slot + 1; if (s1 >= nslots) s1 -= nslots;
       int s2 = base_slot + 2; if (s2 >= nslots) s2 -= nslots;
       const uint32_t so0 = a_base16 + base_slot * slot16;
       const uint32_t so1 = a_base16 + s1 * slot16;
       const uint32_t so2 = a_base16 + s2 * slot16;
-      issue_iteration<MODE, CP, MC, G>(leader, so0, so1, so2, b_base16, dbase);
+      issue_iteration<MODE, CP, MC, G>(leader && !DBG(2), so0, so1, so2, b_base16, dbase);
       if (leader) {
         mma_commit(&tmem_full[buf]);
 #pragma unroll
@@ -343,9 +357,43 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
     constexpr int CPG = CP / 8;
     const int ngroups = P.plain_out ? 1 : min(CPG, (P.Cout - P.n0 + 7) / 8);   // real (non-padding) channel groups
     const long long HWo = (long long)P.Hout * P.Wout;
+    // element stride of one iteration in the output volume (transposed: two output planes per input plane)
+    const size_t it_stride = (size_t)HWo * (P.plain_out ? 1 : 8) * (MODE == MODE_T ? 2 : 1);
+    constexpr int UT = MODE == MODE_T ? 2 * MC * CPG : 1;
+    constexpr int US = MODE == MODE_T ? 1 : (MC >= 2 ? (MC / 2) * CPG : (CPG + 1) / 2);
     int acc_n = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
     TILE_COORDS(tile)
+    // per-tile addressing, hoisted out of the plane loop: offsets of this thread's work units at iteration 0
+    // (they advance by it_stride per iteration) and their validity
+    size_t offsT[UT], offsS[US];
+    bool validT[MC], validS[US];
+    if (MODE == MODE_T) {
+#pragma unroll
+      for (int c = 0; c < MC; ++c) {
+        const int yi = ty0 + c * 4 + q, xi = tx0 + lane;
+        validT[c] = lane < G_::TW && yi < P.Hin && xi < P.Win;
+      }
+#pragma unroll
+      for (int u = 0; u < UT; ++u) {
+        const int k = u / (MC * CPG), c = (u / CPG) % MC, ng = u % CPG;
+        const int pdh = 2 * half + k, pd = pdh >> 1, ph = pdh & 1;
+        const int yi = ty0 + c * 4 + q, xi = tx0 + lane;
+        offsT[u] = g8_offset(b, P.out_g0 + ng, pd, 2 * yi + ph, 2 * xi, P.out_G, P.Dout, P.Hout, P.Wout);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < US; ++u) {
+        const int c = MC >= 2 ? half * (MC / 2) + u / CPG : 0;
+        const int ng = MC >= 2 ? u % CPG : 2 * u + half;
+        const int ty = c * 4 + q, tx = lane;
+        int yo = ty0 + ty, xo;
+        if (MODE == MODE_S1) { xo = tx0 + tx; validS[u] = tx < G_::TW && yo < P.Hout && xo < P.Wout; }
+        else { xo = tx0 + (tx >> 1); validS[u] = !(tx & 1) && (tx >> 1) < G_::TW && yo < P.Hout && xo < P.Wout; }
+        if (P.plain_out) offsS[u] = (size_t)((long long)b * P.Dout * HWo + (long long)yo * P.Wout + xo);
+        else offsS[u] = g8_offset(b, P.out_g0 + ng, 0, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
+      }
+    }
     for (int it = 0; it < niter; ++it, ++acc_n) {
       const int buf = NBUF == 2 ? (acc_n & 1) : 0;
       const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS;
@@ -353,37 +401,27 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
         // units: (class pdh in {2*half, 2*half+1}) x chunk x group; each unit = two adjacent output voxels (x parity)
         constexpr int U = 2 * MC * CPG;
         uint4 sk[U][2];
-        size_t offs[U];
-        bool valid[MC];
-#pragma unroll
-        for (int c = 0; c < MC; ++c) {
-          const int yi = ty0 + c * 4 + q, xi = tx0 + lane;
-          valid[c] = lane < G_::TW && yi < P.Hin && xi < P.Win;
-        }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int k = u / (MC * CPG), c = (u / CPG) % MC, ng = u % CPG;
-          const int pdh = 2 * half + k, pd = pdh >> 1, ph = pdh & 1;
-          const int yi = ty0 + c * 4 + q, xi = tx0 + lane;
-          offs[u] = g8_offset(b, P.out_g0 + ng, 2 * it + pd, 2 * yi + ph, 2 * xi, P.out_G, P.Dout, P.Hout, P.Wout);
-          if (P.skip && valid[c] && ng < ngroups) {
-            sk[u][0] = __ldg(reinterpret_cast<const uint4*>(P.skip + offs[u]));
-            sk[u][1] = __ldg(reinterpret_cast<const uint4*>(P.skip + offs[u] + 8));
+          const int c = (u / CPG) % MC, ng = u % CPG;
+          if (P.skip && validT[c] && ng < ngroups) {
+            sk[u][0] = __ldg(reinterpret_cast<const uint4*>(P.skip + offsT[u]));
+            sk[u][1] = __ldg(reinterpret_cast<const uint4*>(P.skip + offsT[u] + 8));
             // the same voxels two output planes further are next iteration's skip operands: start them towards L1
             // now, a whole iteration ahead (this wait is short when the epilogue is the slower stage)
             if (it + 1 < niter)
-              asm volatile("prefetch.global.L1 [%0];" ::"l"(P.skip + offs[u] + (size_t)2 * P.Hout * P.Wout * 8));
+              asm volatile("prefetch.global.L1 [%0];" ::"l"(P.skip + offsT[u] + it_stride));
           } else {
             sk[u][0] = sk[u][1] = make_uint4(0, 0, 0, 0);
           }
         }
         mbar_wait(&tmem_full[buf], (NBUF == 2 ? (acc_n >> 1) : acc_n) & 1);
         tc_fence_after();
-        if (warp == 2 && lane == 0 && acc_n < 12) TRACE(28 + acc_n);
+        if (warp == 2 && lane == 0 && acc_n < 12) { TRACE(28 + acc_n); }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int k = u / (MC * CPG), c = (u / CPG) % MC, ng = u % CPG;
-          if (ng >= ngroups) continue;   // uniform
+          if (ng >= ngroups || DBG(1)) continue;   // uniform
           const int pdh = 2 * half + k;
           const uint32_t cbase = tbase + (pdh * MC + c) * N + ng * 8;
           uint32_t ya[8], yb[8], yc[8];  // tw = 1 (even x), tw = 2 (odd x, same input), tw = 0 (odd x, input + 1)
@@ -405,38 +443,30 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
             r0.v[j] = a + __uint_as_float((j & 1) ? (w0 & 0xffff0000u) : (w0 << 16));
             r1.v[j] = bb + __uint_as_float((j & 1) ? (w1 & 0xffff0000u) : (w1 << 16));
           }
-          if (valid[c]) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + offs[u];
+          if (validT[c]) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + offsT[u];
             store8(o, r0);
             store8(o + 8, r1);
           }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) offsT[u] += it_stride;
       } else {
-        // units: MC == 2: this half's chunk x all groups; MC == 1: chunk 0, groups ng == half (mod 2)
-        constexpr int U = MC >= 2 ? (MC / 2) * CPG : (CPG + 1) / 2;
+        constexpr int U = US;
         uint4 sk[U];
-        size_t offs[U];
-        bool valid[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int c = MC >= 2 ? half * (MC / 2) + u / CPG : 0;
           const int ng = MC >= 2 ? u % CPG : 2 * u + half;
-          const int ty = c * 4 + q, tx = lane;
-          int yo = ty0 + ty, xo;
-          if (MODE == MODE_S1) { xo = tx0 + tx; valid[u] = tx < G_::TW && yo < P.Hout && xo < P.Wout; }
-          else { xo = tx0 + (tx >> 1); valid[u] = !(tx & 1) && (tx >> 1) < G_::TW && yo < P.Hout && xo < P.Wout; }
-          if (P.plain_out) offs[u] = (size_t)(((long long)b * P.Dout + it) * HWo + (long long)yo * P.Wout + xo);
-          else offs[u] = g8_offset(b, P.out_g0 + ng, it, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
-          sk[u] = (P.skip && valid[u] && ng < ngroups) ? __ldg(reinterpret_cast<const uint4*>(P.skip + offs[u])) : make_uint4(0, 0, 0, 0);
+          sk[u] = (P.skip && validS[u] && ng < ngroups) ? __ldg(reinterpret_cast<const uint4*>(P.skip + offsS[u])) : make_uint4(0, 0, 0, 0);
         }
         mbar_wait(&tmem_full[buf], (NBUF == 2 ? (acc_n >> 1) : acc_n) & 1);
         tc_fence_after();
-        if (warp == 2 && lane == 0 && acc_n < 12) TRACE(28 + acc_n);
+        if (warp == 2 && lane == 0 && acc_n < 12) { TRACE(28 + acc_n); }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           const int c = MC >= 2 ? half * (MC / 2) + u / CPG : 0;
           const int ng = MC >= 2 ? u % CPG : 2 * u + half;
-          if (ng >= ngroups) continue;   // uniform
+          if (ng >= ngroups || DBG(1)) continue;   // uniform
           const uint32_t cbase = tbase + c * N + ng * 8;
           if (P.plain_out) {
             uint32_t y0, y1, y2;
@@ -445,7 +475,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
             tmem_ld1(cbase + 2 * CP, y2);
             tmem_ld_wait();
             const float v = __uint_as_float(y0) + shfl_dn(y1, 1) + shfl_dn(y2, 2);
-            if (valid[u]) reinterpret_cast<float*>(P.out)[offs[u]] = v;
+            if (validS[u]) reinterpret_cast<float*>(P.out)[offsS[u]] = v;
           } else {
             uint32_t y0[8], y1[8], y2[8];
             tmem_ld8(cbase, y0);
@@ -462,14 +492,16 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
               const uint32_t w = sw[j >> 1];
               r.v[j] = a + __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
             }
-            if (valid[u]) store8(reinterpret_cast<__nv_bfloat16*>(P.out) + offs[u], r);
+            if (validS[u]) store8(reinterpret_cast<__nv_bfloat16*>(P.out) + offsS[u], r);
           }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) offsS[u] += it_stride;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
-      if (warp == 2 && lane == 0 && acc_n < 12) TRACE(40 + acc_n);
+      if (warp == 2 && lane == 0 && acc_n < 12) { TRACE(40 + acc_n); }
     }
     }
   }
@@ -642,6 +674,11 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
+static CUtensorMapL2promotion l2_promotion() {
+  static const int v = getenv("DAMVS_TC_L2") ? atoi(getenv("DAMVS_TC_L2")) : 2;   // development knob
+  return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
+
 // G8 bf16 volume [BG][D][H][W*8] viewed with rows (row0, row0 + row_step, ...)
 static int make_map(CUtensorMap* m, const void* base, int BG, int D, int H, int W, int row0, int row_step, int box_rows, int G) {
   EncodeTiledFn fn = encode_fn();
@@ -653,7 +690,7 @@ static int make_map(CUtensorMap* m, const void* base, int BG, int D, int H, int 
   cuuint32_t estr[4] = {1, 1, 1, 1};
   void* addr = (void*)((const uint8_t*)base + (size_t)row0 * W * 16);
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(DAMVS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) W=%d H=%d D=%d BG=%d rows=%d", (int)r, W, H, D, BG, box_rows);
   return DAMVS_OK;
 }
@@ -686,6 +723,10 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   int nslots = (int)((kSmemBudget - fx) / sb);
   const int nplanes = (P.niter - 1) * G_::adv + G_::span;
   if (nslots > kMaxSlots) nslots = kMaxSlots;
+  static const int slot_cap = getenv("DAMVS_TC_SLOTS") ? atoi(getenv("DAMVS_TC_SLOTS")) : 8;   // development knob
+  static const int l2promo = getenv("DAMVS_TC_L2") ? atoi(getenv("DAMVS_TC_L2")) : 2;
+  (void)l2promo;
+  if (nslots > slot_cap) nslots = std::max(slot_cap, G_::span + 1);
   if (nslots < G_::span + 1) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: ring does not fit");
   // leave room for a second CTA per SM when a deep ring is not needed
   while (nslots > G_::span + 1 && fx + (size_t)nslots * sb + 1024 > kSmemBudget / 2) --nslots;
@@ -791,7 +832,11 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
   if (!build_program(mode, G, steps)) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: no program for Cin=%d", d->Cin);
   const int nsteps = (int)steps.size();
   const size_t bb = (blob_bytes(nsteps, CP) + 255) / 256 * 256;
-  const int mc = pick_mc(mode, G, CP, nsteps, mode == MODE_T ? d->Hin : P.Hout, mode == MODE_T ? d->Win : P.Wout, d->B);
+  int mc = pick_mc(mode, G, CP, nsteps, mode == MODE_T ? d->Hin : P.Hout, mode == MODE_T ? d->Win : P.Wout, d->B);
+  static const int mc_force = getenv("DAMVS_TC_MC") ? atoi(getenv("DAMVS_TC_MC")) : 0;   // development knobs
+  static const int dbg = getenv("DAMVS_TC_DBG") ? atoi(getenv("DAMVS_TC_DBG")) : 0;
+  if (mc_force && mc_force < mc && mc_fits(mode, G, CP, nsteps, mc_force)) mc = mc_force;
+  P.dbg = dbg;
   if (mc == 0) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cin=%d Cout=%d does not fit in shared memory", d->Cin, d->Cout);
   for (int k = 0; k < split; ++k) {
     P.blob = (const uint8_t*)packed + k * bb;
