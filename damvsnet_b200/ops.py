@@ -157,6 +157,23 @@ def features_to_nhwc(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def features_to_nhwc_half(x: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] fp32 (any memory format) -> contiguous [B,H,W,C] fp16, saturating (the bf16 pipeline's feature
+    format, damvs_nchw_to_nhwc_f16)."""
+    _need(x, "feature", torch.float32, 4)
+    b, c, h, w = x.shape
+    if c % 8:
+        raise ValueError(f"feature channels {c} must be a multiple of 8")
+    if x.permute(0, 2, 3, 1).is_contiguous() and not x.is_contiguous():
+        # already channels_last: a cast is all that is left (rare path; the reference hands over NCHW)
+        return x.permute(0, 2, 3, 1).clamp(-65504.0, 65504.0).to(torch.float16)
+    x = x.contiguous()
+    out = torch.empty((b, h, w, c), dtype=torch.float16, device=x.device)
+    with torch.cuda.device_of(x):
+        _lib.check(_lib.load().damvs_nchw_to_nhwc_f16(_p(x), _p(out), b, c, h, w, _stream()))
+    return out
+
+
 def compose_projection(proj_pair: torch.Tensor) -> torch.Tensor:
     """[...,2,4,4] -> [...,4,4]: rows 0-2 = K @ E[:3,:4] (reference models/cas_mvsnet.py:44-47)."""
     out = proj_pair[..., 0, :, :].clone()
@@ -207,11 +224,14 @@ def warp_aggregate(ref_nhwc: torch.Tensor, src_nhwc: Sequence[torch.Tensor], rot
                    depth_values: torch.Tensor, wnet: Optional[torch.Tensor], mode: str,
                    out_dtype: torch.dtype) -> G8Volume:
     """Fused warp + aggregation (reference models/cas_mvsnet.py:30-87) -> G8 cost volume."""
-    _need(ref_nhwc, "ref_nhwc", torch.float32, 4)
+    fdt = ref_nhwc.dtype if isinstance(ref_nhwc, torch.Tensor) else None
+    if fdt not in (torch.float32, torch.float16):
+        raise ValueError("features must be fp32 or fp16 NHWC tensors")
+    _need(ref_nhwc, "ref_nhwc", fdt, 4)
     b, h, w, c = ref_nhwc.shape
     n_src = len(src_nhwc)
     for i, s in enumerate(src_nhwc):
-        _need(s, f"src_nhwc[{i}]", torch.float32, 4)
+        _need(s, f"src_nhwc[{i}]", fdt, 4)
         if s.shape != ref_nhwc.shape or not s.is_contiguous():
             raise ValueError("source features must be contiguous and shaped like the reference feature")
     _need(rot_trans, "rot_trans", torch.float32, 3)
@@ -231,10 +251,10 @@ def warp_aggregate(ref_nhwc: torch.Tensor, src_nhwc: Sequence[torch.Tensor], rot
     out = G8Volume.empty(b, c, d, h, w, out_dtype, ref_nhwc.device)
     ptrs = (ctypes.c_void_p * n_src)(*[s.data_ptr() for s in src_nhwc])
     nbytes = (n_src + 1) * b * c * h * w * 4 + dv.numel() * 4 + out.data.numel() * out.data.element_size()
+    fn = _lib.load().damvs_warp_agg_fwd_f16 if fdt == torch.float16 else _lib.load().damvs_warp_agg_fwd
     with torch.cuda.device_of(ref_nhwc), _timed("warp_agg", bytes=float(nbytes)):
-        _lib.check(_lib.load().damvs_warp_agg_fwd(_p(ref_nhwc.contiguous()), ptrs, n_src, _p(rot_trans.contiguous()), _p(dv),
-                                                  _p(wnet), _p(out.data), b, c, d, h, w, m, per_pixel, _dt(out_dtype),
-                                                  _stream()))
+        _lib.check(fn(_p(ref_nhwc.contiguous()), ptrs, n_src, _p(rot_trans.contiguous()), _p(dv),
+                      _p(wnet), _p(out.data), b, c, d, h, w, m, per_pixel, _dt(out_dtype), _stream()))
     return out
 
 

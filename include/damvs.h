@@ -117,6 +117,15 @@ int damvs_conv3d_pack_weight(const damvs_conv3d_desc* desc, const float* weight,
 int damvs_conv3d_fwd(const damvs_conv3d_desc* desc, const void* in, const void* packed, const float* scale,
                      const float* shift, const void* skip, void* out, void* stream);
 
+/* ---- half-precision feature path (the bf16 pipeline's producer) ---------------
+ * Same operation as damvs_nchw_to_nhwc_f32 / damvs_warp_agg_fwd with the feature maps held as fp16 NHWC
+ * (values saturate at +-65504): half the gather traffic, fp32 accumulation in the blend, coordinates equal to
+ * the reference's up to fp32 rounding instead of bit-exact.  Used when the cost volume is emitted in bf16.   */
+int damvs_nchw_to_nhwc_f16(const float* in, void* out, int B, int C, int H, int W, void* stream);
+int damvs_warp_agg_fwd_f16(const void* ref_nhwc, const void* const* src_nhwc, int n_src, const float* rot_trans,
+                           const float* depth_hyp, const float* wnet, void* out_vol, int B, int C, int D, int H,
+                           int W, int mode, int per_pixel_hyp, int out_dtype, void* stream);
+
 /* ---- softmax / regression head -------------------------------------------- */
 /* Replaces models/cas_mvsnet.py:105-124 + depth_regression (models/module.py:609):
  * softmax over D, expected depth, photometric confidence (sum of p over

@@ -7,6 +7,7 @@ from damvsnet_b200 import ops, synthetic
 from damvsnet_b200.runner import HotPathRunner, make_workload
 
 dev = torch.device("cuda:0")
+torch.set_grad_enabled(False)   # inference path (fused kernels), as the runner uses
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 sd = synthetic.hot_path_state_dict(seed=0)

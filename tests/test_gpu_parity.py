@@ -159,6 +159,40 @@ def test_cost_volume_matches_oracle_ragged(dm, mode, C):
     assert ((bf - want).abs() <= want.abs() * 2 ** -7 + 2e-3).all()
 
 
+def test_half_repack_matches_cast(dm):
+    x = torch.randn(2, 16, 19, 23, device=dev()) * 3
+    x[0, 0, 0, 0] = 1e6                      # saturates instead of overflowing to inf
+    y = dm.ops.features_to_nhwc_half(x)
+    want = x.permute(0, 2, 3, 1).clamp(-65504, 65504).to(torch.float16)
+    assert y.dtype == torch.float16 and y.is_contiguous() and torch.equal(y, want)
+    yc = dm.ops.features_to_nhwc_half(x.contiguous(memory_format=torch.channels_last))
+    assert torch.equal(yc, want)
+
+
+@pytest.mark.parametrize("mode", ["adaptive", "variance"])
+@pytest.mark.parametrize("C", [8, 16, 32])
+def test_half_feature_path_matches_oracle(dm, mode, C):
+    """The fp16-feature kernel (the bf16 pipeline's producer) against the oracle on the SAME fp16-rounded
+    features, fp32 volume out: what remains is fp16 bilinear weights (2^-12 relative) and fp32 rounding of
+    the simplified coordinate arithmetic.  Ragged extents, 2 batch items, both hypothesis layouts."""
+    from damvsnet_b200 import synthetic
+    stage = {32: 0, 16: 1, 8: 2}[C]
+    sd = synthetic.hot_path_state_dict(seed=11)
+    feats, pm, dv = synthetic.make_stage_inputs(stage, 2, 4, 4 * 37, 4 * 45, 6, seed=4, channels=C)
+    feats = [f[:, :, :37, :45].contiguous().half().float() for f in feats]
+    dv = dv[:, :, :37, :45].contiguous()
+    net, _ = _build_net(dm, sd, stage, mode)
+    wnet = net.weight_net[stage].folded() if mode == "adaptive" else None
+    rt = net.stage_rot_trans(pm.to(dev()))
+    nhwc = [dm.ops.features_to_nhwc_half(f.to(dev())) for f in feats]
+    for hyp in (dv, dv[:, :, 0, 0].contiguous()):
+        want = O.aggregate(feats, pm, hyp, mode, sd, stage)
+        got = dm.ops.warp_aggregate(nhwc[0], nhwc[1:], rt, hyp.to(dev()), wnet, mode, torch.float32).to_ncdhw().cpu()
+        scale = max(want.abs().mean().item(), 1.0)
+        assert ((got - want).abs() <= 2e-3 * want.abs() + 5e-3 * scale).all()
+        assert (got - want).abs().mean() < 2e-4 * scale
+
+
 def test_variance_of_identical_views_is_zero_full_size(dm):
     """Size-independent property at the BASELINE stage-1 extent: identical views under identity
     relative pose sample themselves (up to the W/(W-1) quirk) -- use a constant feature so the
