@@ -73,34 +73,35 @@ __device__ __forceinline__ FootH make_foot(float ix, float iy, int H, int W) {
   return f;
 }
 
-// acc += tap[k] * w for 8 fp16 channels packed in a uint4; w is the low (HI = false) or high half of `wpair`
+// out = tap * w + in for 8 fp16 channels packed in a uint4 (FHFMA: fp16 operands, fp32 accumulate); w is the low
+// (HI = false) or high half of `wpair`.  out and in may be the same array.
 template <bool HI>
-__device__ __forceinline__ void fhfma8(float (&acc)[8], const uint4& t, uint32_t wpair) {
+__device__ __forceinline__ void fhfma8(float (&out)[8], const float (&in)[8], const uint4& t, uint32_t wpair) {
   const uint32_t tw[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (HI) {
       asm("{.reg .b16 tl, th, wl, wh;\n\t"
-          "mov.b32 {tl, th}, %2;\n\t"
-          "mov.b32 {wl, wh}, %3;\n\t"
-          "fma.rn.f32.f16 %0, tl, wh, %0;\n\t"
-          "fma.rn.f32.f16 %1, th, wh, %1;}"
-          : "+f"(acc[2 * k]), "+f"(acc[2 * k + 1]) : "r"(tw[k]), "r"(wpair));
+          "mov.b32 {tl, th}, %4;\n\t"
+          "mov.b32 {wl, wh}, %5;\n\t"
+          "fma.rn.f32.f16 %0, tl, wh, %2;\n\t"
+          "fma.rn.f32.f16 %1, th, wh, %3;}"
+          : "=f"(out[2 * k]), "=f"(out[2 * k + 1]) : "f"(in[2 * k]), "f"(in[2 * k + 1]), "r"(tw[k]), "r"(wpair));
     } else {
       asm("{.reg .b16 tl, th, wl, wh;\n\t"
-          "mov.b32 {tl, th}, %2;\n\t"
-          "mov.b32 {wl, wh}, %3;\n\t"
-          "fma.rn.f32.f16 %0, tl, wl, %0;\n\t"
-          "fma.rn.f32.f16 %1, th, wl, %1;}"
-          : "+f"(acc[2 * k]), "+f"(acc[2 * k + 1]) : "r"(tw[k]), "r"(wpair));
+          "mov.b32 {tl, th}, %4;\n\t"
+          "mov.b32 {wl, wh}, %5;\n\t"
+          "fma.rn.f32.f16 %0, tl, wl, %2;\n\t"
+          "fma.rn.f32.f16 %1, th, wl, %3;}"
+          : "=f"(out[2 * k]), "=f"(out[2 * k + 1]) : "f"(in[2 * k]), "f"(in[2 * k + 1]), "r"(tw[k]), "r"(wpair));
     }
   }
 }
 
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
-template <int C, int MODE, typename OutT, int DCH>
-__global__ void __launch_bounds__(128) warp_agg_h_kernel(const WarpAggHParams P) {
+template <int C, int MODE, typename OutT, int DCH, bool REUSE, int MINB, bool FULL>
+__global__ void __launch_bounds__(128, MINB) warp_agg_h_kernel(const WarpAggHParams P) {
   constexpr int LPP = C / 8;     // lanes per pixel
   constexpr int PPW = 32 / LPP;  // pixels per warp (along x)
   constexpr int TW = PPW, TH = 4;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(128) warp_agg_h_kernel(const WarpAggHParams P)
       nrf[2 * k] = -f.x; nrf[2 * k + 1] = -f.y;
     }
   }
+  const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const float fx = (float)x, fy = (float)y;
   float2 w1[4];
   float s1 = 0.f, b1 = 0.f, w2 = 0.f, s2 = 0.f, b2 = 0.f;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(128) warp_agg_h_kernel(const WarpAggHParams P)
 #pragma unroll
     for (int k = 0; k < NPJ; ++k) {
       const int j = q + k * LPP, d = d0 + j;
-      dep[k] = (j < DCH && d < D) ? __ldg(hyp + d * hyp_stride) : 1.f;
+      dep[k] = (j < DCH && (FULL || d < D)) ? __ldg(hyp + d * hyp_stride) : 1.f;
     }
     for (int v = 0; v < n_src; ++v) {
       const float* rt = s_rt + v * 12;
@@ -200,7 +202,7 @@ __global__ void __launch_bounds__(128) warp_agg_h_kernel(const WarpAggHParams P)
       uint4 t00 = make_uint4(0, 0, 0, 0), t01 = t00, t10 = t00, t11 = t00;
 #pragma unroll
       for (int j = 0; j < DCH; ++j) {
-        if (d0 + j < D) {  // uniform
+        if (FULL || d0 + j < D) {  // uniform
           FootH f;
           if (LPP > 1) {
             const uint4 u = s_fp[warp][j][pw];
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(128) warp_agg_h_kernel(const WarpAggHParams P)
           } else {
             f = fp[j];
           }
-          if (f.off != cur) {
+          if (!REUSE || f.off != cur) {
             const char* p = img + f.off;
             t00 = ldg16(p);
             t01 = ldg16(p + C * 2);
@@ -216,13 +218,12 @@ __global__ void __launch_bounds__(128) warp_agg_h_kernel(const WarpAggHParams P)
             t11 = ldg16(p + (size_t)W * (C * 2) + C * 2);
             cur = f.off;
           }
-          float df[8];   // warp - ref  (variance mode: warp, see below)
-#pragma unroll
-          for (int k = 0; k < 8; ++k) df[k] = MODE == DAMVS_AGG_VARIANCE ? 0.f : nrf[k];
-          fhfma8<false>(df, t00, f.w01);
-          fhfma8<true>(df, t01, f.w01);
-          fhfma8<false>(df, t10, f.w23);
-          fhfma8<true>(df, t11, f.w23);
+          float df[8];   // warp - ref  (variance mode: warp)
+          if (MODE == DAMVS_AGG_VARIANCE) fhfma8<false>(df, zero8, t00, f.w01);
+          else fhfma8<false>(df, nrf, t00, f.w01);
+          fhfma8<true>(df, df, t01, f.w01);
+          fhfma8<false>(df, df, t10, f.w23);
+          fhfma8<true>(df, df, t11, f.w23);
           if (MODE == DAMVS_AGG_VARIANCE) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -253,7 +254,7 @@ __global__ void __launch_bounds__(128) warp_agg_h_kernel(const WarpAggHParams P)
     }
 #pragma unroll
     for (int j = 0; j < DCH; ++j) {
-      if (d0 + j < D) {
+      if (FULL || d0 + j < D) {
         F8 r;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -320,15 +321,23 @@ __global__ void __launch_bounds__(128) nchw_to_nhwc_f16_kernel(const float* __re
   }
 }
 
+// Per channel width: depth chunk, tap reuse and minimum CTAs per SM (measured at the DTU-test stage shapes on B200:
+// unconditional tap loads let the compiler batch a chunk's gathers, which beats skipping repeated 2x2 blocks; the
+// narrow kernels trade accumulators for occupancy).
+template <int C> struct HCfg { static constexpr int DCH = 4, MINB = 1; };
+template <> struct HCfg<32> { static constexpr int DCH = 4, MINB = 5; };
+template <> struct HCfg<16> { static constexpr int DCH = 2, MINB = 6; };
+template <> struct HCfg<8> { static constexpr int DCH = 2, MINB = 8; };
+
 template <int C, int MODE>
 static int launch_h(const WarpAggHParams& P, int out_dtype, cudaStream_t st) {
   constexpr int TW = 32 / (C / 8), TH = 4;
+  constexpr int DCH = HCfg<C>::DCH, MINB = HCfg<C>::MINB;
   dim3 grid((P.W + TW - 1) / TW, (P.H + TH - 1) / TH, P.B);
-  static const int cfg = getenv("DAMVS_WARP_CFG") ? atoi(getenv("DAMVS_WARP_CFG")) : 0;   // development knob
-  if (out_dtype == DAMVS_F32) warp_agg_h_kernel<C, MODE, float, 4><<<grid, 128, 0, st>>>(P);
-  else if (cfg == 2) warp_agg_h_kernel<C, MODE, __nv_bfloat16, 2><<<grid, 128, 0, st>>>(P);
-  else if (cfg == 8) warp_agg_h_kernel<C, MODE, __nv_bfloat16, 8><<<grid, 128, 0, st>>>(P);
-  else warp_agg_h_kernel<C, MODE, __nv_bfloat16, 4><<<grid, 128, 0, st>>>(P);
+  const bool full = P.D % DCH == 0;
+  if (out_dtype == DAMVS_F32) warp_agg_h_kernel<C, MODE, float, DCH, false, 1, false><<<grid, 128, 0, st>>>(P);
+  else if (full) warp_agg_h_kernel<C, MODE, __nv_bfloat16, DCH, false, MINB, true><<<grid, 128, 0, st>>>(P);
+  else warp_agg_h_kernel<C, MODE, __nv_bfloat16, DCH, false, MINB, false><<<grid, 128, 0, st>>>(P);
   DAMVS_LAUNCH_OK("warp_agg_h kernel");
   return DAMVS_OK;
 }
