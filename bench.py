@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--detail", action="store_true", help="print a per-layer device-time table to stderr")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--inflight", type=int, default=3, help="independent views in flight on separate streams (graph mode)")
     return ap.parse_args()
 
 
@@ -199,7 +200,7 @@ def run_ours(args):
 
     import damvsnet_b200 as dm
     from damvsnet_b200 import _lib, synthetic
-    from damvsnet_b200.runner import HotPathRunner, make_workload
+    from damvsnet_b200.runner import HotPathRunner, ViewPipeline, make_workload
     _lib.check(_lib.load().damvs_check_device(local))
     dm.set_precision(args.precision, args.conv_impl)
     nd = [int(x) for x in args.ndepths.split(",")]
@@ -214,9 +215,25 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     steps, warmup = max(args.steps, 1), max(args.warmup, 3)
-    step_fn = runner.run_device if args.no_graph else runner.run_device_graphed
-    for _ in range(warmup):
-        step_fn(dev_stages)
+    inflight = 1 if args.no_graph else max(1, args.inflight)
+    pipe = None
+    if not args.no_graph:
+        # K independent views in flight: K input sets (distinct data), one captured graph + stream each
+        sets = [dev_stages] + [[([f.to(dev) for f in fs], p.to(dev), d.to(dev)) for fs, p, d in
+                                make_workload(args.height, args.width, args.nviews, nd, seed=1000 * (k + 1) + rank)]
+                               for k in range(inflight - 1)]
+        pipe = ViewPipeline(runner, sets)
+
+    def run_views(n):
+        if pipe is None:
+            for _ in range(n):
+                runner.run_device(dev_stages)
+        else:
+            pipe.fork()
+            pipe.submit(n)
+            pipe.join()
+
+    run_views(max(warmup, inflight))
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -224,8 +241,7 @@ def run_ours(args):
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(steps):
-        step_fn(dev_stages)
+    run_views(steps)
     e1.record()
     barrier()
     launches = (_lib.launch_count() - l0) // steps
@@ -299,10 +315,14 @@ def run_ours(args):
             k = kernels[tag]
             avg_ms = k["ms_per_step"] / k["launches_per_step"]
             if tag.startswith("conv3d"):
-                return {"kernel": tag, "bound": "tensor", "achieved": k["TFLOPs"], "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
-                        "frac": k["TFLOPs"] / pk["tensor_sustained"], "traffic": traffic.get(tag),
-                        "peak_source": pk["src"] + " (sustained bf16: kernel timed inside the step)", "avg_launch_ms": avg_ms,
-                        "also_hbm": {"achieved": k["GBps"], "peak": pk["hbm"], "unit": "GB/s", "frac": k["GBps"] / pk["hbm"]}}
+                # arithmetic intensity of the layer-by-layer CostRegNet is ~100 flop/B, below the ridge
+                # (sustained bf16 / HBM = 207 flop/B): the HBM roof is the binding one; the tensor roof is reported beside it
+                ai = (k["TFLOPs"] * 1e12) / max(k["GBps"] * 1e9, 1.0)
+                return {"kernel": tag, "bound": "hbm", "achieved": k["GBps"], "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": k["GBps"] / pk["hbm"], "traffic": traffic.get(tag), "peak_source": pk["src"], "avg_launch_ms": avg_ms,
+                        "arithmetic_intensity_flop_per_byte": ai, "ridge_flop_per_byte": pk["tensor_sustained"] * 1e3 / pk["hbm"],
+                        "also_tensor": {"achieved": k["TFLOPs"], "peak": pk["tensor_sustained"], "unit": "TFLOP/s",
+                                        "frac": k["TFLOPs"] / pk["tensor_sustained"], "peak_source": pk["src"] + " (sustained bf16)"}}
             return {"kernel": tag, "bound": "hbm", "achieved": k["GBps"], "peak": pk["hbm"], "unit": "GB/s",
                     "frac": k["GBps"] / pk["hbm"], "traffic": traffic.get(tag), "peak_source": pk["src"], "avg_launch_ms": avg_ms}
 
@@ -319,7 +339,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic", "config": config_of(args, {"parallelism": f"views sharded x{world}, no data-path collective",
-                                                                          "launch": "eager" if args.no_graph else "cuda-graph replay of the 3-stage step"}),
+                                                                          "launch": "eager" if args.no_graph else f"cuda-graph replay of the 3-stage step, {inflight} independent views in flight on {inflight} streams"}),
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "rooflines": rooflines if rank == 0 else None, "kernels": kernels,
                 "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
