@@ -60,6 +60,7 @@ _SIGNATURES = {
                                      POINTER(c_void_p), c_void_p] + [c_int] * 6 + [c_void_p]),
     "damvs_warp_weighted_bwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                         c_void_p, POINTER(c_void_p), c_void_p] + [c_int] * 6 + [c_void_p]),
+    "damvs_uncertainty_samples_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "damvs_launch_count": (c_uint64, []),
 }
 

@@ -17,7 +17,8 @@ from __future__ import annotations
 import importlib
 from typing import Dict, List
 
-HOT_NAMES = ("homo_warping", "depth_regression", "Conv3d", "Deconv3d", "CostRegNet", "AggWeightNetVolume")
+HOT_NAMES = ("homo_warping", "depth_regression", "Conv3d", "Deconv3d", "CostRegNet", "AggWeightNetVolume",
+             "uncertainty_aware_samples")
 
 _saved: Dict[str, Dict[str, object]] = {}
 

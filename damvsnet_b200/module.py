@@ -24,7 +24,8 @@ from . import autograd as ag
 from . import ops
 from .ops import G8Volume
 
-__all__ = ["Conv3d", "Deconv3d", "CostRegNet", "AggWeightNetVolume", "homo_warping", "depth_regression"]
+__all__ = ["Conv3d", "Deconv3d", "CostRegNet", "AggWeightNetVolume", "homo_warping", "depth_regression",
+           "uncertainty_aware_samples"]
 
 
 def _bn_affine(bn: nn.BatchNorm3d) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -338,3 +339,20 @@ def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tenso
     if depth_values.dim() == 1:
         depth_values = depth_values.view(1, -1).expand(p.shape[0], -1)
     return ops.depth_regression(p, depth_values.to(torch.float32))
+
+
+def uncertainty_aware_samples(cur_depth: torch.Tensor, exp_var: torch.Tensor, ndepth, dtype=None, device=None, shape=None) -> torch.Tensor:
+    """Reference signature (models/module.py:999): cur_depth [B,Dtot] (first stage) or [B,1,H,W], exp_var [B,1,H,W]
+    -> depth hypotheses [B,D,H,W].  The [B,1,H,W] branch runs the native kernel (at the inputs' own resolution);
+    the first-stage branch is a [B,D] range broadcast over (H,W), as in the reference.  No gradient flows into
+    the samples (the reference detaches depth and variance under grad_method="detach", cas_mvsnet.py:237-239)."""
+    ndepth = int(ndepth)
+    if cur_depth.dim() == 2:
+        lo, hi = cur_depth[:, 0], cur_depth[:, -1]
+        interval = (hi - lo) / (ndepth - 1)
+        rng = lo.unsqueeze(1) + torch.arange(0, ndepth, device=cur_depth.device, dtype=cur_depth.dtype).reshape(1, -1) * interval.unsqueeze(1)
+        return rng.unsqueeze(-1).unsqueeze(-1).repeat(1, 1, shape[1], shape[2])
+    if cur_depth.dim() != 4 or cur_depth.shape[1] != 1 or exp_var.shape != cur_depth.shape:
+        raise ValueError("cur_depth and exp_var must be [B,1,H,W]")
+    b, _, h, w = cur_depth.shape
+    return ops.stage_hypotheses(cur_depth.detach().reshape(b, h, w).float(), exp_var.detach().reshape(b, h, w).float(), ndepth, h, w, 1)

@@ -329,6 +329,24 @@ def softmax_regress(logits: torch.Tensor, depth_values: torch.Tensor, want_prob:
     return prob, depth, conf, var
 
 
+def stage_hypotheses(prev_depth: torch.Tensor, prev_var: torch.Tensor, ndepth: int, height: int, width: int,
+                     scale: int) -> torch.Tensor:
+    """Fused hypothesis sampling for cascade stages 2/3: previous-stage depth / variance [B,hp,wp] ->
+    depth_values [B,D,height/scale,width/scale] (reference models/cas_mvsnet.py:250-253, 269-274, 293-296 +
+    models/module.py:1012-1036 in one kernel)."""
+    _need(prev_depth, "prev_depth", torch.float32, 3)
+    _need(prev_var, "prev_var", torch.float32, 3)
+    if prev_var.shape != prev_depth.shape:
+        raise ValueError("prev_depth and prev_var must have the same shape")
+    assert ndepth > 1
+    b, hp, wp = prev_depth.shape
+    out = torch.empty((b, ndepth, height // scale, width // scale), dtype=torch.float32, device=prev_depth.device)
+    with torch.cuda.device_of(prev_depth):
+        _lib.check(_lib.load().damvs_uncertainty_samples_fwd(_p(prev_depth.contiguous()), _p(prev_var.contiguous()), _p(out), b, hp, wp,
+                                                             ndepth, height, width, scale, _stream()))
+    return out
+
+
 def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tensor:
     _need(p, "p", torch.float32, 4)
     p = p.contiguous()

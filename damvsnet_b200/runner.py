@@ -56,6 +56,36 @@ class HotPathRunner:
     def run_device(self, stages: Sequence[StageInput]) -> List[Dict[str, torch.Tensor]]:
         return [self.run_stage(i, f, p, d) for i, (f, p, d) in enumerate(stages)]
 
+    # ------------------------------------------------------------------ chained cascade
+    @torch.no_grad()
+    def run_cascade(self, features: Sequence[Sequence[torch.Tensor]], proj_matrices: Dict[str, torch.Tensor],
+                    depth_values: torch.Tensor, ndepths: Sequence[int], height: int, width: int,
+                    scales: Sequence[int] = synthetic.STAGE_SCALES) -> Dict[str, object]:
+        """The stage loop of CascadeMVSNet.forward (reference models/cas_mvsnet.py:210-307) on given per-stage
+        features: stage-1 hypotheses from the plane-sweep range, stages 2/3 from the previous stage's depth and
+        variance through the fused sampling kernel, every stage through DepthNet.  `features[s]` is the list of N
+        stage-s feature maps (the reference refines the reference-view features between stages with its PyTorch
+        GeoFeatureFusionNet; pass the refined maps in if that is wanted).  Returns the reference's output dict:
+        "stage1".."stage3" plus the last stage's five keys at top level (cas_mvsnet.py:306-307)."""
+        from . import ops
+        outputs: Dict[str, object] = {}
+        depth = var = None
+        for s, nd in enumerate(ndepths):
+            f = features[s]
+            b, _, h, w = f[0].shape
+            if depth is None:
+                lo, hi = depth_values[:, 0], depth_values[:, -1]
+                rng = lo.unsqueeze(1) + torch.arange(nd, device=depth_values.device, dtype=torch.float32).view(1, -1) * \
+                    ((hi - lo) / (nd - 1)).unsqueeze(1)                         # module.py:1003-1008
+                dv = rng.view(b, nd, 1, 1).expand(b, nd, h, w).contiguous()
+            else:
+                dv = ops.stage_hypotheses(depth, var, nd, height, width, scales[s])
+            out = self.run_stage(s, f, proj_matrices[f"stage{s + 1}"], dv)
+            depth, var = out["depth"], out["variance"]
+            outputs[f"stage{s + 1}"] = out
+            outputs.update(out)
+        return outputs
+
     # ------------------------------------------------------------------ CUDA-graph replay
     @staticmethod
     def _signature(stages: Sequence[StageInput]):

@@ -213,6 +213,17 @@ int damvs_warp_weighted_bwd(const float* ref_nhwc, const float* const* src_nhwc,
                             float* const* g_src, float* g_wt_vol, int B, int C, int D, int H, int W, int per_pixel_hyp,
                             void* stream);
 
+/* ---- depth-hypothesis sampling for cascade stages 2/3 (upstream neighbour of the path) ----------------
+ * Fuses models/cas_mvsnet.py:250-253 (two bilinear up-samples to full resolution), uncertainty_aware_samples
+ * (models/module.py:999-1038, the `cur_depth.dim() != 2` branch) and the trilinear resample of
+ * models/cas_mvsnet.py:293-296 into one kernel:
+ *   prev_depth, prev_var  device [B,hp,wp] fp32: `depth` and `variance` of the previous stage
+ *   out                   device [B,D,H/scale,W/scale] fp32: the depth_values DepthNet.forward receives
+ * (H,W) is the full image size, scale in {1,2,4} the stage scale.  With hp = H, wp = W, scale = 1 it is
+ * uncertainty_aware_samples alone on full-resolution [B,1,H,W] inputs.                                   */
+int damvs_uncertainty_samples_fwd(const float* prev_depth, const float* prev_var, float* out, int B, int hp, int wp, int D,
+                                  int H, int W, int scale, void* stream);
+
 /* Number of kernel launches this library has issued in this process (for bench.py's gpu_launches). */
 uint64_t damvs_launch_count(void);
 

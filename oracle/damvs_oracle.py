@@ -249,6 +249,43 @@ def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tenso
 
 
 # --------------------------------------------------------------------------
+# depth-hypothesis sampling (upstream neighbour of the path)
+# --------------------------------------------------------------------------
+HYP_EPS = 1e-12  # reference models/module.py:10
+
+
+def uncertainty_aware_samples(cur_depth: torch.Tensor, exp_var: torch.Tensor, ndepth: int) -> torch.Tensor:
+    """cur_depth, exp_var [B,1,H,W] -> hypotheses [B,D,H,W].  Reference models/module.py:1012-1036 (the
+    `cur_depth.dim() != 2` branch), without the Python lists: the D planes are one broadcast."""
+    low = -torch.min(cur_depth, exp_var)
+    step = (exp_var - low) / (float(ndepth) - 1)
+    i = torch.arange(ndepth, dtype=cur_depth.dtype).view(1, ndepth, 1, 1)
+    lin = low + step * i
+    offset = F.softmax(3 * lin / (exp_var + HYP_EPS), dim=1)
+    return cur_depth + lin + HYP_EPS + offset * step
+
+
+def first_stage_samples(depth_values: torch.Tensor, ndepth: int) -> torch.Tensor:
+    """depth_values [B,Dtot] -> [B,D] evenly spaced over its range.  Reference models/module.py:1003-1010
+    (spatially constant, so the repeat and the resample of the caller are the identity on every pixel)."""
+    lo, hi = depth_values[:, 0], depth_values[:, -1]
+    interval = (hi - lo) / (ndepth - 1)
+    return lo.unsqueeze(1) + torch.arange(ndepth, dtype=depth_values.dtype).view(1, -1) * interval.unsqueeze(1)
+
+
+def stage_hypotheses(prev_depth: torch.Tensor, prev_var: torch.Tensor, ndepth: int, height: int, width: int,
+                     scale: int) -> torch.Tensor:
+    """[B,hp,wp] depth / variance of the previous stage -> depth_values [B,D,height/scale,width/scale] handed to
+    DepthNet.forward.  Reference models/cas_mvsnet.py:250-253 (bilinear to full resolution), :269-274,
+    :293-296 (trilinear to the stage resolution), all with align_corners=False."""
+    cur = F.interpolate(prev_depth.unsqueeze(1), [height, width], mode="bilinear", align_corners=False)
+    ev = F.interpolate(prev_var.unsqueeze(1), [height, width], mode="bilinear", align_corners=False)
+    full = uncertainty_aware_samples(cur, ev, ndepth)
+    return F.interpolate(full.unsqueeze(1), [ndepth, height // scale, width // scale], mode="trilinear",
+                         align_corners=False).squeeze(1)
+
+
+# --------------------------------------------------------------------------
 # whole stage
 # --------------------------------------------------------------------------
 def depthnet_forward(stage_idx: int, features: List[torch.Tensor], proj_matrices: torch.Tensor,

@@ -60,3 +60,9 @@ def load_train_grads(mode: str, bn_mode: str):
         elif k.startswith(tag + "out/"):
             out["out"][k[len(tag) + 4:]] = t(npz[k])
     return out
+
+
+def load_hypotheses():
+    """Hypothesis-sampling fixture (tests/golden/make_golden_hyp.py)."""
+    npz = np.load(os.path.join(GOLDEN, "hypotheses.npz"))
+    return {k: torch.from_numpy(np.asarray(npz[k])) for k in npz.files}

@@ -209,6 +209,37 @@ def test_variance_of_identical_views_is_zero_full_size(dm):
     assert inner.abs().max().item() < 1e-6
 
 
+# ---------------------------------------------------------------- hypothesis sampling (upstream neighbour)
+def test_stage_hypotheses_match_reference_fixture(dm):
+    fx = golden_io.load_hypotheses()
+    for name in ("stage2", "stage3"):
+        H, W, scale, D = (int(v) for v in fx[name + "/meta"])
+        got = dm.ops.stage_hypotheses(fx[name + "/depth"].to(dev()), fx[name + "/var"].to(dev()), D, H, W, scale).cpu()
+        assert got.shape == fx[name + "/out"].shape
+        torch.testing.assert_close(got, fx[name + "/out"], rtol=2e-6, atol=2e-3)
+        # reference-signature entry point on full-resolution [B,1,H,W] inputs
+        cur = torch.nn.functional.interpolate(fx[name + "/depth"].unsqueeze(1), [H, W], mode="bilinear", align_corners=False)
+        ev = torch.nn.functional.interpolate(fx[name + "/var"].unsqueeze(1), [H, W], mode="bilinear", align_corners=False)
+        full = dm.uncertainty_aware_samples(cur.to(dev()), ev.to(dev()), D, torch.float32, dev(), [2, H, W]).cpu()
+        torch.testing.assert_close(full[:, :, ::3, ::3], fx[name + "/full_sub"], rtol=2e-6, atol=2e-3)
+    first = dm.uncertainty_aware_samples(fx["stage1/depth_values"].to(dev()), None, 48, torch.float32, dev(), [2, 64, 96]).cpu()
+    torch.testing.assert_close(first[:, :, ::16, ::16], fx["stage1/out"], rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("scale,D", [(1, 8), (2, 32), (4, 48)])
+def test_stage_hypotheses_match_oracle_full_size(dm, scale, D):
+    """BASELINE shapes (1152x1600): previous stage at half the output stage's pitch; monotone hypotheses."""
+    g = torch.Generator().manual_seed(scale)
+    H, W = 1152, 1600
+    hp, wp = H // (2 * scale) if scale < 4 else H // 4, W // (2 * scale) if scale < 4 else W // 4
+    depth = 450 + 400 * torch.rand(1, hp, wp, generator=g)
+    var = 0.2 + 8 * torch.rand(1, hp, wp, generator=g)
+    got = dm.ops.stage_hypotheses(depth.to(dev()), var.to(dev()), D, H, W, scale).cpu()
+    want = O.stage_hypotheses(depth, var, D, H, W, scale)
+    torch.testing.assert_close(got, want, rtol=2e-6, atol=2e-3)
+    assert (got[:, 1:] >= got[:, :-1]).all()
+
+
 # ---------------------------------------------------------------- conv blocks
 def _rand_bn(bn, g):
     with torch.no_grad():
@@ -343,6 +374,36 @@ def test_depthnet_batch2_seven_views_default_depths(dm, stage, D):
     span = (dv.max(1).values - dv.min(1).values).clamp_min(1e-3)
     nrm = (out16["depth"].cpu() - want["depth"]).abs() / span
     assert nrm.median().item() < 2.5e-3 and torch.quantile(nrm.flatten(), 0.99).item() < 3e-2
+
+
+def test_runner_cascade_chains_stages_like_the_oracle(dm):
+    """Three stages chained through the native hypothesis sampler (fp32 mode) against the same chain in the oracle."""
+    from damvsnet_b200 import synthetic
+    from damvsnet_b200.runner import HotPathRunner
+    H, W, N, nds = 64, 96, 3, [16, 8, 8]
+    sd = synthetic.hot_path_state_dict(seed=3)
+    feats = [synthetic.make_stage_inputs(s, 1, N, H, W, nds[s], seed=6)[0] for s in range(3)]
+    projs, _ = synthetic.make_cameras(1, N, H, W, seed=6)
+    dvals = synthetic.make_depth_range(1, 192)
+    runner = HotPathRunner(sd, device=dev())
+    with dm.precision("fp32"):
+        got = runner.run_cascade([[f.to(dev()) for f in fs] for fs in feats], {k: v.to(dev()) for k, v in projs.items()},
+                                 dvals.to(dev()), nds, H, W)
+    depth = var = None
+    for s in range(3):
+        h, w = H // synthetic.STAGE_SCALES[s], W // synthetic.STAGE_SCALES[s]
+        if depth is None:
+            dv = O.first_stage_samples(dvals, nds[s]).view(1, nds[s], 1, 1).expand(1, nds[s], h, w).contiguous()
+        else:
+            dv = O.stage_hypotheses(depth, var, nds[s], H, W, synthetic.STAGE_SCALES[s])
+        want = O.depthnet_forward(s, feats[s], projs[f"stage{s + 1}"], dv, sd, "adaptive")
+        depth, var = want["depth"], want["variance"]
+        g = got[f"stage{s + 1}"]
+        assert _rel(g["depth_values"].cpu(), dv).max() < 1e-5
+        # errors compound through the chain: the stage-3 hypotheses hang off the stage-1/2 estimates
+        assert _rel(g["depth"].cpu(), want["depth"]).max() < 1e-4 * (1 + 2 * s)
+    assert set(got) == {"stage1", "stage2", "stage3", "depth", "photometric_confidence", "variance", "prob_volume", "depth_values"}
+    assert got["depth"] is got["stage3"]["depth"]
 
 
 def test_runner_graph_replay_matches_eager(dm):

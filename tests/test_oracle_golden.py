@@ -95,3 +95,18 @@ def test_oracle_against_live_reference_depthnet():
     assert _conf_ok(got["photometric_confidence"], want["photometric_confidence"])
     # the synthetic weights must give a non-degenerate head
     assert want["prob_volume"].max(1).values.mean().item() > 0.15
+
+
+def test_hypothesis_sampling_matches_reference_fixture():
+    from tests.golden_io import load_hypotheses
+    fx = load_hypotheses()
+    for name in ("stage2", "stage3"):
+        H, W, scale, D = (int(v) for v in fx[name + "/meta"])
+        cur = torch.nn.functional.interpolate(fx[name + "/depth"].unsqueeze(1), [H, W], mode="bilinear", align_corners=False)
+        ev = torch.nn.functional.interpolate(fx[name + "/var"].unsqueeze(1), [H, W], mode="bilinear", align_corners=False)
+        torch.testing.assert_close(O.uncertainty_aware_samples(cur, ev, D)[:, :, ::3, ::3], fx[name + "/full_sub"], rtol=1e-6, atol=1e-4)
+        got = O.stage_hypotheses(fx[name + "/depth"], fx[name + "/var"], D, H, W, scale)
+        torch.testing.assert_close(got, fx[name + "/out"], rtol=1e-6, atol=1e-4)
+    first = O.first_stage_samples(fx["stage1/depth_values"], 48)
+    want = fx["stage1/out"]
+    torch.testing.assert_close(first.view(2, 48, 1, 1).expand_as(want), want, rtol=1e-6, atol=1e-4)
