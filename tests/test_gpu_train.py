@@ -183,3 +183,31 @@ def test_eval_no_grad_path_unchanged_by_training_code(dm):
         b = net(0, [f.clone().requires_grad_(True) for f in fs], fx["proj"].to(dev()), fx["depth_values"].to(dev()), 8, cr)
     assert rel(b["depth"].detach().cpu(), a["depth"].cpu()) < 1e-5
     assert rel(b["prob_volume"].detach().cpu(), a["prob_volume"].cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,stride,transposed", [
+    (8, 8, 1, False), (16, 8, 1, False), (32, 8, 1, False), (64, 64, 1, False), (8, 1, 1, False),
+    (8, 16, 2, False), (16, 32, 2, False), (32, 64, 2, False),
+    (64, 32, 2, True), (32, 16, 2, True), (16, 8, 2, True)])
+def test_weight_gradient_kernels_match_torch(dm, cin, cout, stride, transposed):
+    """damvs_conv3d_wgrad (tensor-core kernel for bf16 volumes, CUDA-core kernel for fp32) against autograd of
+    F.conv3d / F.conv_transpose3d on the same (bf16-rounded) operands; ragged extents, 2 batch items."""
+    import torch.nn.functional as F
+    from damvsnet_b200 import ops_train
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    B, D, H, W = 2, 6, 10, 38
+    x = torch.randn(B, cin, D, H, W, generator=g).bfloat16().float()
+    w = torch.randn((cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3), generator=g).requires_grad_(True)
+    y = F.conv_transpose3d(x, w, None, stride=2, padding=1, output_padding=1) if transposed else F.conv3d(x, w, None, stride=stride, padding=1)
+    gy = torch.randn(y.shape, generator=g).bfloat16().float()
+    (y * gy).sum().backward()
+    gy_p = gy
+    if cout % 8:
+        gy_p = torch.zeros(B, 8, *gy.shape[2:])
+        gy_p[:, :cout] = gy
+    for dtype, tol in ((torch.bfloat16, 2e-3), (torch.float32, 1e-4)):
+        xv = dm.G8Volume.from_ncdhw(x.to(dev()), dtype).data
+        gv = dm.G8Volume.from_ncdhw(gy_p.to(dev()), dtype).data
+        dw = ops_train.conv3d_wgrad(xv, gv, cin, cout, stride, transposed).cpu()
+        assert dw.shape == w.shape
+        assert rel(dw, w.grad) < tol, (dtype, rel(dw, w.grad))
