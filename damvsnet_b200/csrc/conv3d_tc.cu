@@ -595,12 +595,20 @@ static bool build_program(int mode, int G, std::vector<StepSrc>& steps) {
   return ok && (int)steps.size() <= kMaxSteps;
 }
 
+// depth-folded variant for stride-1 layers with <= 16 output channels (conv3d_tcf.cu)
+bool conv3d_tcf_supported(const damvs_conv3d_desc* d);
+size_t conv3d_tcf_packed_bytes(const damvs_conv3d_desc* d);
+int conv3d_tcf_pack(const damvs_conv3d_desc* d, const float* weight, void* packed, cudaStream_t st);
+int conv3d_tcf_launch(const damvs_conv3d_desc* d, const void* in, const void* packed, const float* scale, const float* shift,
+                      const void* skip, void* out, cudaStream_t st);
+
 // how many output-channel blobs a layer is split into so that weights + ring fit in shared memory
 static int n_split(int Cin, int Cout) { return (Cin >= 64 && Cout >= 64) ? 2 : 1; }
 
 static size_t blob_bytes(int nsteps, int CP) { return (size_t)weights_offset(nsteps) + (size_t)nsteps * 2 * 3 * CP * 16; }
 
 size_t conv3d_tc_packed_bytes(const damvs_conv3d_desc* d) {
+  if (conv3d_tcf_supported(d)) return conv3d_tcf_packed_bytes(d);
   std::vector<StepSrc> steps;
   if (!build_program(mode_of(d), d->Cin / 8, steps)) return 0;
   int split = n_split(d->Cin, d->Cout);
@@ -631,6 +639,7 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, uint8_t* __re
 }
 
 int conv3d_tc_pack(const damvs_conv3d_desc* d, const float* weight, void* packed, cudaStream_t st) {
+  if (conv3d_tcf_supported(d)) return conv3d_tcf_pack(d, weight, packed, st);
   std::vector<StepSrc> steps;
   const int mode = mode_of(d), G = d->Cin / 8;
   if (!build_program(mode, G, steps)) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cin=%d not supported", d->Cin);
@@ -813,6 +822,7 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
   if (d->in_dtype != DAMVS_BF16 || (!d->plain_out && d->out_dtype != DAMVS_BF16))
     return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: bf16 volumes only");
   if (d->plain_out && (d->transposed || d->stride != 1)) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: plain_out is stride-1 only");
+  if (conv3d_tcf_supported(d)) return conv3d_tcf_launch(d, in, packed, scale, shift, skip, out, st);
   const int mode = mode_of(d), G = d->Cin / 8;
   if (G != 1 && G % 2) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cin=%d not supported", d->Cin);
   if (d->Cout > 64) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cout=%d > 64", d->Cout);
