@@ -152,7 +152,7 @@ def features_to_nhwc(x: torch.Tensor) -> torch.Tensor:
     x = x.contiguous()
     b, c, h, w = x.shape
     out = torch.empty((b, h, w, c), dtype=torch.float32, device=x.device)
-    with torch.cuda.device_of(x):
+    with torch.cuda.device_of(x), _timed("repack", bytes=float(x.numel() * 8)):
         _lib.check(_lib.load().damvs_nchw_to_nhwc_f32(_p(x), _p(out), b, c, h, w, _stream()))
     return out
 
@@ -169,7 +169,7 @@ def features_to_nhwc_half(x: torch.Tensor) -> torch.Tensor:
         return x.permute(0, 2, 3, 1).clamp(-65504.0, 65504.0).to(torch.float16)
     x = x.contiguous()
     out = torch.empty((b, h, w, c), dtype=torch.float16, device=x.device)
-    with torch.cuda.device_of(x):
+    with torch.cuda.device_of(x), _timed("repack", bytes=float(x.numel() * 4 + out.numel() * 2)):
         _lib.check(_lib.load().damvs_nchw_to_nhwc_f16(_p(x), _p(out), b, c, h, w, _stream()))
     return out
 
