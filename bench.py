@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--detail", action="store_true", help="print a per-layer device-time table to stderr")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--inflight", type=int, default=3, help="independent views in flight on separate streams (graph mode)")
+    ap.add_argument("--inflight", type=int, default=4, help="independent views in flight on separate streams (graph mode)")
     return ap.parse_args()
 
 

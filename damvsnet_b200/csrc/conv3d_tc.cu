@@ -73,6 +73,7 @@ struct TcParams {
   int out_G, out_g0;  // output volume's group count and first group written by this launch
   int n0, Cout, relu, plain_out, niter, nsteps, nslots;
   int tiles_x, tiles_y, ntiles;  // persistent CTAs walk tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+  int zchunks, zlen;             // a tile covers zlen iterations (depth planes) of one of zchunks depth ranges
   unsigned long long* trace;  // development aid: per-CTA event timestamps (null in production)
   int dbg;                    // development aid (DAMVS_TC_DBG, trace builds only): bit0 skip epilogue body, bit1 skip MMA issue, bit2 skip loads
 };
@@ -235,9 +236,12 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile -> (batch item, tile origin); origins are output coords for S1/S2, input coords for T
 #define TILE_COORDS(tile_)                                               \
-  const int b = (tile_) / (P.tiles_x * P.tiles_y);                       \
-  const int ty0 = (((tile_) / P.tiles_x) % P.tiles_y) * TH;              \
-  const int tx0 = ((tile_) % P.tiles_x) * G_::TW;
+  const int t2_ = (tile_) / P.zchunks;                                   \
+  const int it0 = ((tile_) - t2_ * P.zchunks) * P.zlen;                  \
+  const int nit = min(P.zlen, P.niter - it0);                            \
+  const int b = t2_ / (P.tiles_x * P.tiles_y);                           \
+  const int ty0 = ((t2_ / P.tiles_x) % P.tiles_y) * TH;                  \
+  const int tx0 = (t2_ % P.tiles_x) * G_::TW;
 
   if (threadIdx.x == 0) { TRACE(0); }
   // ---- one-time setup ------------------------------------------------------------------------
@@ -272,11 +276,11 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const int nplanes = (niter - 1) * G_::adv + G_::span;
       const uint32_t bytes = (uint32_t)(patch0_bytes + patch1_bytes);
       int slot = 0, round = 0;
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       TILE_COORDS(tile)
+      const int nplanes = (nit - 1) * G_::adv + G_::span;
       for (int k = 0; k < nplanes; ++k) {
         if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
         if (DBG(4)) {   // development aid: no loads, the MMAs run on whatever the ring holds
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
         }
         mbar_arrive_expect_tx(&full[slot], bytes);
         uint8_t* dst = sA + slot * slot_stride;
-        const int plane = k + G_::p0;
+        const int plane = it0 * G_::adv + k + G_::p0;
         if (MODE == MODE_S1) {
           tma_load_4d(dst, &map0, &full[slot], (tx0 - 1) * 8, ty0 - 1, plane, b * G);
         } else if (MODE == MODE_T) {
@@ -309,7 +313,8 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
     int acc_n = 0;                                           // accumulator buffers handed to the epilogue so far
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
     int next_wait = 0;
-    for (int it = 0; it < niter; ++it, ++acc_n) {
+    const int nit = min(P.zlen, P.niter - (tile % P.zchunks) * P.zlen);
+    for (int it = 0; it < nit; ++it, ++acc_n) {
       const int need = it * G_::adv + G_::span - 1;
       while (next_wait <= need) {
         mbar_wait(&full[wait_slot], wait_round & 1);
@@ -394,7 +399,11 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
         else offsS[u] = g8_offset(b, P.out_g0 + ng, 0, yo, xo, P.out_G, P.Dout, P.Hout, P.Wout);
       }
     }
-    for (int it = 0; it < niter; ++it, ++acc_n) {
+#pragma unroll
+    for (int u = 0; u < UT; ++u) offsT[u] += (size_t)it0 * it_stride;
+#pragma unroll
+    for (int u = 0; u < US; ++u) offsS[u] += (size_t)it0 * it_stride;
+    for (int it = 0; it < nit; ++it, ++acc_n) {
       const int buf = NBUF == 2 ? (acc_n & 1) : 0;
       const uint32_t tbase = tmem_base + ((uint32_t)(32 * q) << 16) + buf * ACC_COLS;
       if (MODE == MODE_T) {
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
             sk[u][1] = __ldg(reinterpret_cast<const uint4*>(P.skip + offsT[u] + 8));
             // the same voxels two output planes further are next iteration's skip operands: start them towards L1
             // now, a whole iteration ahead (this wait is short when the epilogue is the slower stage)
-            if (it + 1 < niter)
+            if (it + 1 < nit)
               asm volatile("prefetch.global.L1 [%0];" ::"l"(P.skip + offsT[u] + it_stride));
           } else {
             sk[u][0] = sk[u][1] = make_uint4(0, 0, 0, 0);
@@ -747,7 +756,22 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   const int tiles_h = MODE == MODE_T ? d->Hin : P.Hout, tiles_w = MODE == MODE_T ? d->Win : P.Wout;
   P.tiles_x = (tiles_w + G_::TW - 1) / G_::TW;
   P.tiles_y = (tiles_h + TH - 1) / TH;
-  P.ntiles = P.tiles_x * P.tiles_y * d->B;
+  // very few spatial tiles (the bottleneck level of stage 1): split the depth range so that more SMs get work; each
+  // chunk re-loads span - adv halo planes.  Measured: splitting every layer with < 2 tiles per SM helps one view in
+  // flight (3.54 -> 3.48 ms) and costs throughput with 3-4 views in flight (more CTAs contending), hence the low bar.
+  {
+    const int spatial = P.tiles_x * P.tiles_y * d->B;
+    static const int zsplit_off = getenv("DAMVS_TC_NO_ZSPLIT") != nullptr;   // development knob
+    int zc = 1;
+    if (!zsplit_off && spatial * 2 < 148) {
+      const int want = (148 + spatial - 1) / spatial;
+      const int min_len = spatial * 4 < 148 ? 1 : 2;
+      zc = std::max(1, std::min(want, P.niter / min_len));
+    }
+    P.zlen = (P.niter + zc - 1) / zc;
+    P.zchunks = (P.niter + P.zlen - 1) / P.zlen;
+    P.ntiles = spatial * P.zchunks;
+  }
   // persistent grid: as many CTAs as fit at once (shared memory, TMEM columns, registers)
   DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   cudaFuncAttributes fa;
