@@ -439,3 +439,32 @@ def test_runner_host_pipeline_matches_device(dm):
             for k in ("depth", "photometric_confidence", "variance"):
                 assert torch.equal(a[k].cpu(), b[k]), k
         runner.release(t)
+
+
+def test_tanks_and_temples_shape_seven_views_invariants(dm):
+    """BASELINE.json configs[2] (1056x1920, N=7, D=48/32/8) at full size, where the oracle is too slow: size-independent
+    properties of the three stages in the benchmarked bf16 mode -- probabilities sum to one, the regressed depth lies
+    inside its pixel's hypothesis range, confidence in [0,1], variance >= 0, everything finite -- and agreement of the
+    bf16 pipeline with the exact fp32 pipeline on the same inputs (median error normalised by the hypothesis span)."""
+    from damvsnet_b200 import synthetic
+    from damvsnet_b200.runner import HotPathRunner, make_workload
+    sd = synthetic.hot_path_state_dict(seed=0)
+    runner = HotPathRunner(sd, device=dev())
+    stages = make_workload(1056, 1920, 7, [48, 32, 8], seed=2, device=dev())
+    with dm.precision("bf16"):
+        outs = runner.run_device(stages)
+    with dm.precision("fp32"):
+        ref = runner.run_stage(2, *stages[2])
+    for (f, p, d), o in zip(stages, outs):
+        assert len(f) == 7
+        for k in ("depth", "photometric_confidence", "variance", "prob_volume"):
+            assert torch.isfinite(o[k]).all(), k
+        assert (o["prob_volume"].sum(1) - 1).abs().max() < 1e-4
+        lo, hi = d.min(1).values, d.max(1).values
+        assert (o["depth"] >= lo - 1e-3).all() and (o["depth"] <= hi + 1e-3).all()
+        assert (o["photometric_confidence"] >= 0).all() and (o["photometric_confidence"] <= 1 + 1e-5).all()
+        assert (o["variance"] >= 0).all()
+    d3 = stages[2][2]
+    span = (d3.max(1).values - d3.min(1).values).clamp_min(1e-6)
+    err = ((outs[2]["depth"] - ref["depth"]).abs() / span)
+    assert err.median() < 2.5e-3 and err.quantile(0.99) < 3e-2
