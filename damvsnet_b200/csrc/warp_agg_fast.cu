@@ -278,9 +278,16 @@ __global__ void __launch_bounds__(128, MINB) warp_agg_h_kernel(const WarpAggHPar
 // 16-byte stores are contiguous -- reads its 8 channels (pitch 129 makes the 32 lanes hit 32 different banks).
 constexpr int kTP = 128;
 constexpr int kTPitch = kTP + 1;
-__global__ void __launch_bounds__(128) nchw_to_nhwc_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, int C,
-                                                               long long HW, int tiles_per_cta) {
+constexpr int kMaxRepack = 16;
+struct RepackPtrs {
+  const float* in[kMaxRepack];
+  __half* out[kMaxRepack];
+};
+__global__ void __launch_bounds__(128) nchw_to_nhwc_f16_kernel(const __grid_constant__ RepackPtrs ptrs, int C, long long HW,
+                                                               int tiles_per_cta) {
   extern __shared__ float ftile[];  // [C][kTPitch]
+  const float* __restrict__ in = ptrs.in[blockIdx.z];
+  __half* __restrict__ out = ptrs.out[blockIdx.z];
   const int b = blockIdx.y, t = threadIdx.x;
   const bool vec = (HW % 4 == 0);
   const int cpp = C / 8;
@@ -346,18 +353,31 @@ static int launch_h(const WarpAggHParams& P, int out_dtype, cudaStream_t st) {
 
 using namespace damvs;
 
-extern "C" int damvs_nchw_to_nhwc_f16(const float* in, void* out, int B, int C, int H, int W, void* stream) {
-  DAMVS_REQUIRE(in && out, "nchw_to_nhwc_f16: null pointer");
+extern "C" int damvs_nchw_to_nhwc_f16_multi(const float* const* ins, void* const* outs, int n, int B, int C, int H, int W, void* stream) {
+  DAMVS_REQUIRE(ins && outs, "nchw_to_nhwc_f16: null pointer");
+  DAMVS_REQUIRE(n >= 1 && n <= kMaxRepack, "nchw_to_nhwc_f16: n=%d outside [1,%d]", n, kMaxRepack);
   DAMVS_REQUIRE(B > 0 && B <= 65535 && C > 0 && C % 8 == 0 && C <= 256 && H > 0 && W > 0, "nchw_to_nhwc_f16: bad shape (C must be a multiple of 8)");
-  DAMVS_REQUIRE(aligned16(in) && aligned16(out), "nchw_to_nhwc_f16: pointers must be 16-byte aligned");
+  RepackPtrs ptrs{};
+  for (int i = 0; i < n; ++i) {
+    DAMVS_REQUIRE(ins[i] && outs[i] && aligned16(ins[i]) && aligned16(outs[i]), "nchw_to_nhwc_f16: tensor %d null or not 16-byte aligned", i);
+    ptrs.in[i] = ins[i];
+    ptrs.out[i] = (__half*)outs[i];
+  }
   const long long HW = (long long)H * W;
   const long long tiles = (HW + kTP - 1) / kTP;
-  const int tiles_per_cta = tiles > 148 * 32 ? 4 : 1;
-  dim3 grid((unsigned)((tiles + tiles_per_cta - 1) / tiles_per_cta), B);
+  const int tiles_per_cta = tiles * n > 148 * 32 ? 2 : 1;
+  dim3 grid((unsigned)((tiles + tiles_per_cta - 1) / tiles_per_cta), B, n);
   const size_t smem = (size_t)C * kTPitch * sizeof(float);
-  nchw_to_nhwc_f16_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(in, (__half*)out, C, HW, tiles_per_cta);
+  if (smem > 48 * 1024) DAMVS_CUDA_OK(cudaFuncSetAttribute(nchw_to_nhwc_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  nchw_to_nhwc_f16_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(ptrs, C, HW, tiles_per_cta);
   DAMVS_LAUNCH_OK("nchw_to_nhwc_f16 kernel");
   return DAMVS_OK;
+}
+
+extern "C" int damvs_nchw_to_nhwc_f16(const float* in, void* out, int B, int C, int H, int W, void* stream) {
+  const float* ins[1] = {in};
+  void* outs[1] = {out};
+  return damvs_nchw_to_nhwc_f16_multi(ins, outs, 1, B, C, H, W, stream);
 }
 
 extern "C" int damvs_warp_agg_fwd_f16(const void* ref_nhwc, const void* const* src_nhwc, int n_src, const float* rot_trans,

@@ -174,6 +174,22 @@ def features_to_nhwc_half(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def features_to_nhwc_half_multi(xs: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+    """features_to_nhwc_half for the N views of a stage in ONE launch (equal shapes, plain NCHW); anything else goes
+    through the per-tensor path."""
+    x0 = xs[0]
+    if len(xs) > 16 or any((not isinstance(x, torch.Tensor)) or x.shape != x0.shape or x.dtype != torch.float32 or not x.is_cuda
+                           or not x.is_contiguous() for x in xs) or x0.dim() != 4 or x0.shape[1] % 8:
+        return [features_to_nhwc_half(x) for x in xs]
+    b, c, h, w = x0.shape
+    outs = [torch.empty((b, h, w, c), dtype=torch.float16, device=x0.device) for _ in xs]
+    ins_p = (ctypes.c_void_p * len(xs))(*[x.data_ptr() for x in xs])
+    outs_p = (ctypes.c_void_p * len(xs))(*[o.data_ptr() for o in outs])
+    with torch.cuda.device_of(x0), _timed("repack", bytes=float(len(xs) * x0.numel() * 6)):
+        _lib.check(_lib.load().damvs_nchw_to_nhwc_f16_multi(ins_p, outs_p, len(xs), b, c, h, w, _stream()))
+    return outs
+
+
 def compose_projection(proj_pair: torch.Tensor) -> torch.Tensor:
     """[...,2,4,4] -> [...,4,4]: rows 0-2 = K @ E[:3,:4] (reference models/cas_mvsnet.py:44-47)."""
     out = proj_pair[..., 0, :, :].clone()

@@ -122,6 +122,8 @@ int damvs_conv3d_fwd(const damvs_conv3d_desc* desc, const void* in, const void* 
  * (values saturate at +-65504): half the gather traffic, fp32 accumulation in the blend, coordinates equal to
  * the reference's up to fp32 rounding instead of bit-exact.  Used when the cost volume is emitted in bf16.   */
 int damvs_nchw_to_nhwc_f16(const float* in, void* out, int B, int C, int H, int W, void* stream);
+/* n (<= 16) equally shaped feature maps in one launch; ins / outs are HOST arrays of device pointers. */
+int damvs_nchw_to_nhwc_f16_multi(const float* const* ins, void* const* outs, int n, int B, int C, int H, int W, void* stream);
 int damvs_warp_agg_fwd_f16(const void* ref_nhwc, const void* const* src_nhwc, int n_src, const float* rot_trans,
                            const float* depth_hyp, const float* wnet, void* out_vol, int B, int C, int D, int H,
                            int W, int mode, int per_pixel_hyp, int out_dtype, void* stream);
