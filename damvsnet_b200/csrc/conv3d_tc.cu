@@ -782,6 +782,8 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   constexpr int NEEDC = (2 * ACC <= 512 ? 2 : 1) * ACC;
   constexpr int TCOLS = NEEDC <= 32 ? 32 : NEEDC <= 64 ? 64 : NEEDC <= 128 ? 128 : NEEDC <= 256 ? 256 : 512;
   occ = std::max(1, std::min(occ, 512 / TCOLS));
+  static const int occ_cap = getenv("DAMVS_TC_OCC") ? atoi(getenv("DAMVS_TC_OCC")) : 8;   // development knob
+  occ = std::min(occ, occ_cap);
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
   dim3 grid((unsigned)std::min(P.ntiles, occ * num_sms), 1, 1);

@@ -363,7 +363,8 @@ static int launch_g(const damvs_conv3d_desc* d, Params& P, const void* in, cudaS
   P.ntiles = P.tiles_x * P.tiles_y * d->B;
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
-  dim3 grid((unsigned)std::min(P.ntiles, 2 * num_sms), 1, 1);
+  static const int occ_cap = getenv("DAMVS_TC_OCC") ? atoi(getenv("DAMVS_TC_OCC")) : 2;   // development knob
+  dim3 grid((unsigned)std::min(P.ntiles, std::min(2, occ_cap) * num_sms), 1, 1);
   kern<<<grid, 320, smem, st>>>(m0, P);
   DAMVS_LAUNCH_OK("conv3d_tcf kernel");
   return DAMVS_OK;

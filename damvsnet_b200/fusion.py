@@ -1,0 +1,70 @@
+"""Geometric-consistency filtering of a reference view (the downstream neighbour of the hot path).
+
+Host-side mirror of what reference ``filter/dypcd.py:filter_depth`` does per reference view (lines 205-257, calling
+``check_geometric_consistency`` :135-159 and ``reproject_with_depth`` :98-132): the depth maps stay on the GPU, one
+native kernel (``damvs_geo_consistency_fuse``) replaces the numpy + ``cv2.remap`` loop over source views, and the
+PFM round trip through disk between ``test_uni.py:246-287`` and the filter goes away.  Camera products are formed in
+float64 numpy exactly as the reference forms them.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import _p, _stream
+
+MAX_SRC_VIEWS = 10
+
+
+def pack_cameras(ref_K: np.ndarray, ref_E: np.ndarray, src_Ks: Sequence[np.ndarray], src_Es: Sequence[np.ndarray]) -> np.ndarray:
+    """float64 vector in the layout damvs_geo_consistency_fuse expects (include/damvs.h)."""
+    ref_K, ref_E = np.asarray(ref_K, np.float64), np.asarray(ref_E, np.float64)
+    out = [ref_K.reshape(-1), np.linalg.inv(ref_K).reshape(-1)]
+    for K, E in zip(src_Ks, src_Es):
+        K, E = np.asarray(K, np.float64), np.asarray(E, np.float64)
+        out += [np.matmul(E, np.linalg.inv(ref_E))[:3].reshape(-1), K.reshape(-1), np.linalg.inv(K).reshape(-1),
+                np.matmul(ref_E, np.linalg.inv(E))[:3].reshape(-1)]
+    return np.ascontiguousarray(np.concatenate(out))
+
+
+def filter_reference_view(ref_depth: torch.Tensor, confidences: Sequence[torch.Tensor], ref_K, ref_E,
+                          src_depths: Sequence[torch.Tensor], src_Ks, src_Es, conf_thr: Sequence[float] = (0.1, 0.15, 0.9),
+                          dist_base: float = 1 / 4, rel_diff_base: float = 1 / 1300) -> Dict[str, torch.Tensor]:
+    """ref_depth [H,W] and confidences (stage 1, 2, 3, each [H,W]) of the reference view, src_depths n x [H,W], all CUDA
+    fp32; intrinsics 3x3 / extrinsics 4x4 as numpy.  Returns depth_est_averaged (fp32) and the photo / geo / final masks
+    (bool) of filter/dypcd.py:254-262.  Defaults are the reference's (test_uni.py:104-109)."""
+    n = len(src_depths)
+    if not 1 <= n <= MAX_SRC_VIEWS:
+        raise ValueError(f"1..{MAX_SRC_VIEWS} source views supported (the reference's mask list covers dy_range <= 11)")
+    h, w = ref_depth.shape
+    tensors = [ref_depth, *confidences, *src_depths]
+    if len(confidences) != 3 or any(t.dtype != torch.float32 or not t.is_cuda or tuple(t.shape) != (h, w) for t in tensors):
+        raise ValueError("expected CUDA fp32 [H,W] maps: depth, three confidences, n source depths")
+    tensors = [t.contiguous() for t in tensors]
+    cams = pack_cameras(ref_K, ref_E, src_Ks, src_Es)
+    dev = ref_depth.device
+    depth_avg = torch.empty((h, w), dtype=torch.float32, device=dev)
+    photo, geo, final = (torch.empty((h, w), dtype=torch.uint8, device=dev) for _ in range(3))
+    src_ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tensors[4:]])
+    with torch.cuda.device_of(ref_depth):
+        _lib.check(_lib.load().damvs_geo_consistency_fuse(
+            _p(tensors[0]), _p(tensors[1]), _p(tensors[2]), _p(tensors[3]), src_ptrs,
+            cams.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), n, h, w, float(conf_thr[0]), float(conf_thr[1]), float(conf_thr[2]),
+            float(dist_base), float(rel_diff_base), _p(depth_avg), _p(photo), _p(geo), _p(final), _stream()))
+    return {"depth_est_averaged": depth_avg, "photo_mask": photo.bool(), "geo_mask": geo.bool(), "final_mask": final.bool()}
+
+
+def backproject_valid(depth: torch.Tensor, mask: torch.Tensor, K, E) -> torch.Tensor:
+    """World-space points of the masked pixels, [n,3] (filter/dypcd.py:281-299): inv(E) [inv(K) [x,y,1] d; 1]."""
+    ys, xs = torch.nonzero(mask, as_tuple=True)
+    d = depth[ys, xs].double()
+    pix = torch.stack([xs.double() * d, ys.double() * d, d], 0)
+    Ki = torch.from_numpy(np.linalg.inv(np.asarray(K, np.float64))).to(depth.device)
+    Ei = torch.from_numpy(np.linalg.inv(np.asarray(E, np.float64))).to(depth.device)
+    cam = Ki @ pix
+    world = Ei[:3, :3] @ cam + Ei[:3, 3:4]
+    return world.t().float()

@@ -226,6 +226,20 @@ int damvs_warp_weighted_bwd(const float* ref_nhwc, const float* const* src_nhwc,
 int damvs_uncertainty_samples_fwd(const float* prev_depth, const float* prev_var, float* out, int B, int hp, int wp, int D,
                                   int H, int W, int scale, void* stream);
 
+/* ---- geometric-consistency filtering of one reference view (downstream neighbour of the path) ----------
+ * Fuses reproject_with_depth + check_geometric_consistency (filter/dypcd.py:98-159) and the accumulation over
+ * the source views of filter_depth (filter/dypcd.py:205-257) into one kernel.
+ *   depth_ref, conf1..3  device [H,W] fp32: the reference view's depth and its stage-1/2/3 confidence maps
+ *   depth_src            HOST array of n_src device pointers, [H,W] fp32 each
+ *   cams                 HOST float64: K_ref[9], inv(K_ref)[9], then per source view 42 values:
+ *                        (E_src inv(E_ref)) rows 0-2 [12], K_src [9], inv(K_src) [9], (E_ref inv(E_src)) rows 0-2 [12]
+ *   conf_thr1..3         photometric thresholds (args.conf), dist_base / rel_diff_base the dynamic-consistency bases
+ *   depth_avg [H,W] fp32, photo_mask / geo_mask / final_mask [H,W] uint8 out;  n_src <= 10                     */
+int damvs_geo_consistency_fuse(const float* depth_ref, const float* conf1, const float* conf2, const float* conf3,
+                               const float* const* depth_src, const double* cams, int n_src, int H, int W,
+                               float conf_thr1, float conf_thr2, float conf_thr3, double dist_base, double rel_diff_base,
+                               float* depth_avg, uint8_t* photo_mask, uint8_t* geo_mask, uint8_t* final_mask, void* stream);
+
 /* Number of kernel launches this library has issued in this process (for bench.py's gpu_launches). */
 uint64_t damvs_launch_count(void);
 

@@ -286,6 +286,80 @@ def stage_hypotheses(prev_depth: torch.Tensor, prev_var: torch.Tensor, ndepth: i
 
 
 # --------------------------------------------------------------------------
+# geometric-consistency filtering (downstream neighbour of the path)
+# --------------------------------------------------------------------------
+def remap_bilinear(img, x, y):
+    """cv2.remap(img, x, y, interpolation=cv2.INTER_LINEAR) for float32 single-channel images and float32 maps
+    (default BORDER_CONSTANT, value 0), restated in numpy from OpenCV's published algorithm (the dependency is
+    third party: opencv-python 4.x, modules/imgproc/src/imgwarp.cpp remapBilinear; the reference calls it at
+    filter/dypcd.py:118): map coordinates are rounded to 1/32 pixel (cvRound = round half to even), the four
+    weights are float32 products of the 1-D table entries, taps outside the image contribute 0."""
+    import numpy as np
+    h, w = img.shape
+    sx = np.rint(x.astype(np.float32) * np.float32(32)).astype(np.int64)
+    sy = np.rint(y.astype(np.float32) * np.float32(32)).astype(np.int64)
+    ix, iy = sx >> 5, sy >> 5
+    fx = (sx & 31).astype(np.float32) / np.float32(32)
+    fy = (sy & 31).astype(np.float32) / np.float32(32)
+    out = np.zeros(x.shape, np.float32)
+    for dyy, dxx, wt in ((0, 0, (1 - fx) * (1 - fy)), (0, 1, fx * (1 - fy)), (1, 0, (1 - fx) * fy), (1, 1, fx * fy)):
+        xx, yy = ix + dxx, iy + dyy
+        ok = (xx >= 0) & (xx < w) & (yy >= 0) & (yy < h)
+        tap = np.where(ok, img[np.clip(yy, 0, h - 1), np.clip(xx, 0, w - 1)], np.float32(0))
+        out = out + tap.astype(np.float32) * wt.astype(np.float32)
+    return out
+
+
+def check_geometric_consistency(depth_ref, K_ref, E_ref, depth_src, K_src, E_src, dist_base=1 / 4, rel_diff_base=1 / 1300):
+    """Reference filter/dypcd.py:98-159 (reproject_with_depth + check_geometric_consistency) in numpy, same
+    promotions (float64 projections, float32 where the reference casts).  Returns (masks[9], depth_reprojected)."""
+    import numpy as np
+    height, width = depth_ref.shape
+    x_ref, y_ref = np.meshgrid(np.arange(0, width), np.arange(0, height))
+    xr, yr = x_ref.reshape([-1]), y_ref.reshape([-1])
+    xyz_ref = np.matmul(np.linalg.inv(K_ref), np.vstack((xr, yr, np.ones_like(xr))) * depth_ref.reshape([-1]))
+    xyz_src = np.matmul(np.matmul(E_src, np.linalg.inv(E_ref)), np.vstack((xyz_ref, np.ones_like(xr))))[:3]
+    k_xyz_src = np.matmul(K_src, xyz_src)
+    xy_src = k_xyz_src[:2] / k_xyz_src[2:3]
+    x_src = xy_src[0].reshape([height, width]).astype(np.float32)
+    y_src = xy_src[1].reshape([height, width]).astype(np.float32)
+    sampled = remap_bilinear(depth_src, x_src, y_src)
+    xyz_src = np.matmul(np.linalg.inv(K_src), np.vstack((xy_src, np.ones_like(xr))) * sampled.reshape([-1]))
+    xyz_rep = np.matmul(np.matmul(E_ref, np.linalg.inv(E_src)), np.vstack((xyz_src, np.ones_like(xr))))[:3]
+    depth_rep = xyz_rep[2].reshape([height, width]).astype(np.float32)
+    k_xyz_rep = np.matmul(K_ref, xyz_rep)
+    k_xyz_rep[2:3][k_xyz_rep[2:3] == 0] += 0.00001
+    xy_rep = k_xyz_rep[:2] / k_xyz_rep[2:3]
+    x_rep = xy_rep[0].reshape([height, width]).astype(np.float32)
+    y_rep = xy_rep[1].reshape([height, width]).astype(np.float32)
+    dist = np.sqrt((x_rep - x_ref) ** 2 + (y_rep - y_ref) ** 2)
+    rel = np.abs(depth_rep - depth_ref) / depth_ref
+    masks = [np.logical_and(dist < i * dist_base, rel < i * rel_diff_base) for i in range(2, 11)]
+    depth_rep[~masks[-1]] = 0
+    return masks, depth_rep
+
+
+def filter_reference_view(depth_ref, confs, K_ref, E_ref, depth_srcs, K_srcs, E_srcs, conf_thr=(0.1, 0.15, 0.9),
+                          dist_base=1 / 4, rel_diff_base=1 / 1300):
+    """Per-reference-view part of filter_depth (reference filter/dypcd.py:205-257)."""
+    import numpy as np
+    photo = np.logical_and(np.logical_and(confs[2] > conf_thr[2], confs[1] > conf_thr[1]), confs[0] > conf_thr[0])
+    dy_range = len(depth_srcs) + 1
+    geo_sum, sums, reps = 0, [0] * (dy_range - 2), []
+    for d, K, E in zip(depth_srcs, K_srcs, E_srcs):
+        masks, rep = check_geometric_consistency(depth_ref, K_ref, E_ref, d, K, E, dist_base, rel_diff_base)
+        geo_sum = geo_sum + masks[-1].astype(np.int32)
+        for i in range(2, dy_range):
+            sums[i - 2] = sums[i - 2] + masks[i - 2].astype(np.int32)
+        reps.append(rep)
+    avg = (sum(reps) + depth_ref) / (geo_sum + 1)
+    geo = geo_sum >= dy_range
+    for i in range(2, dy_range):
+        geo = np.logical_or(geo, sums[i - 2] >= i)
+    return {"depth_est_averaged": avg, "photo_mask": photo, "geo_mask": geo, "final_mask": np.logical_and(photo, geo)}
+
+
+# --------------------------------------------------------------------------
 # whole stage
 # --------------------------------------------------------------------------
 def depthnet_forward(stage_idx: int, features: List[torch.Tensor], proj_matrices: torch.Tensor,

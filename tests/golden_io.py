@@ -66,3 +66,9 @@ def load_hypotheses():
     """Hypothesis-sampling fixture (tests/golden/make_golden_hyp.py)."""
     npz = np.load(os.path.join(GOLDEN, "hypotheses.npz"))
     return {k: torch.from_numpy(np.asarray(npz[k])) for k in npz.files}
+
+
+def load_fusion_filter():
+    """Geometric-consistency filter fixture (tests/golden/make_golden_filter.py), numpy arrays keyed 'a/...', 'b/...'."""
+    npz = np.load(os.path.join(GOLDEN, "fusion_filter.npz"))
+    return {k: np.asarray(npz[k]) for k in npz.files}
