@@ -64,6 +64,9 @@ _SIGNATURES = {
     "damvs_uncertainty_samples_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "damvs_geo_consistency_fuse": (c_int, [c_void_p] * 4 + [POINTER(c_void_p), POINTER(c_double), c_int, c_int, c_int, c_float, c_float, c_float,
                                            c_double, c_double] + [c_void_p] * 5),
+    "damvs_cross_view_terms": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "damvs_cross_view_select": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p]),
+    "damvs_cross_view_bwd": (c_int, [c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "damvs_launch_count": (c_uint64, []),
 }
 

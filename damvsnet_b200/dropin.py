@@ -18,7 +18,7 @@ import importlib
 from typing import Dict, List
 
 HOT_NAMES = ("homo_warping", "depth_regression", "Conv3d", "Deconv3d", "CostRegNet", "AggWeightNetVolume",
-             "uncertainty_aware_samples")
+             "uncertainty_aware_samples", "cross_view_loss")
 
 _saved: Dict[str, Dict[str, object]] = {}
 

@@ -240,6 +240,22 @@ int damvs_geo_consistency_fuse(const float* depth_ref, const float* conf1, const
                                float conf_thr1, float conf_thr2, float conf_thr3, double dist_base, double rel_diff_base,
                                float* depth_avg, uint8_t* photo_mask, uint8_t* geo_mask, uint8_t* final_mask, void* stream);
 
+/* ---- cross-view photometric loss (training-side neighbour of the path) -----------------------------------
+ * Fuses cross_view_loss (models/module.py:624-691) and inverse_warping (models/homography.py:7-201) for one stage:
+ *   depth_est, depth_gt  device [B,H,W] fp32
+ *   view_imgs            HOST array of n_src device pointers, [B,3,H,W] fp32 (source images at the stage resolution)
+ *   cams                 device [B][n_src][21] fp32: inv(K_ref) [9], rows 0-2 of [K_ref|0;0001][R_rel|t_rel;0001] [12]
+ * terms:  maskbits [B,H,W] uint16 out (bit v: both warps of source view v valid), sums[v] += smooth-L1 sum (fp64,
+ *         ACCUMULATED; L_v = sums[v] / (B*H*W*3)).
+ * select: counts[v] += number of pixels that pick view v among their two smallest valid L_v (ACCUMULATED).
+ * bwd:    g_depth [B,H,W] out = sum_v coeff[v] * d(smooth-L1 sum of view v)/d depth_est  (coeff: device [n_src]).   */
+int damvs_cross_view_terms(const float* depth_est, const float* depth_gt, const float* const* view_imgs, const float* cams,
+                           int B, int n_src, int H, int W, uint16_t* maskbits, double* sums, void* stream);
+int damvs_cross_view_select(const uint16_t* maskbits, const float* losses, int n_src, long long npix,
+                            unsigned long long* counts, void* stream);
+int damvs_cross_view_bwd(const float* depth_est, const float* depth_gt, const float* const* view_imgs, const float* cams,
+                         const float* coeff, int B, int n_src, int H, int W, float* g_depth, void* stream);
+
 /* Number of kernel launches this library has issued in this process (for bench.py's gpu_launches). */
 uint64_t damvs_launch_count(void);
 

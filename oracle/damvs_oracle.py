@@ -360,6 +360,88 @@ def filter_reference_view(depth_ref, confs, K_ref, E_ref, depth_srcs, K_srcs, E_
 
 
 # --------------------------------------------------------------------------
+# cross-view photometric loss (training-side neighbour of the path)
+# --------------------------------------------------------------------------
+def inverse_warping(img: torch.Tensor, left_cam: torch.Tensor, right_cam: torch.Tensor, depth: torch.Tensor):
+    """img [B,H,W,C] of the source ("right") view warped into the reference ("left") view with the reference
+    depth [B,1,H,W]; cams [B,2,4,4].  Returns (warped [B,H,W,C], mask [B,H,W,1]).
+
+    Restates reference models/homography.py:7-201 without its ``.cuda()`` calls, quirks kept: the source pixel is
+    projected with the REFERENCE intrinsics (:53-57), ``z + 1e-10`` in the perspective divide (:99-100), the
+    bilinear weights use the CLAMPED x1 / y1 (:156-159, :188-191), the mask tests ``y0 <= max_y`` instead of
+    ``y1`` (:153)."""
+    R_l, R_r = left_cam[:, 0, :3, :3], right_cam[:, 0, :3, :3]
+    t_l, t_r = left_cam[:, 0, :3, 3:4], right_cam[:, 0, :3, 3:4]
+    K_l = left_cam[:, 1, :3, :3]
+    K_l_inv = torch.inverse(K_l)
+    R_rel = torch.matmul(R_r, R_l.permute(0, 2, 1))
+    t_rel = t_r - torch.matmul(R_rel, t_l)
+    b, h, w, c = img.shape
+    filler = torch.tensor([0.0, 0.0, 0.0, 1.0]).reshape(1, 1, 4).repeat(b, 1, 1)
+    transform = torch.cat([torch.cat([R_rel, t_rel], dim=2).float(), filler], dim=1)
+    intr = torch.cat([torch.cat([K_l.float(), torch.zeros(b, 3, 1)], dim=2), filler], dim=1)
+    proj = torch.matmul(intr, transform)
+    x_t = torch.matmul(torch.ones(h, 1), torch.linspace(-1.0, 1.0, w).unsqueeze(1).permute(1, 0))
+    y_t = torch.matmul(torch.linspace(-1.0, 1.0, h).unsqueeze(1), torch.ones(1, w))
+    x_t = (x_t + 1.0) * 0.5 * (w - 1)
+    y_t = (y_t + 1.0) * 0.5 * (h - 1)
+    grid = torch.cat([x_t.reshape(1, -1), y_t.reshape(1, -1), torch.ones(1, h * w)], dim=0).unsqueeze(0).repeat(b, 1, 1)
+    cam = torch.matmul(K_l_inv.float(), grid.float()) * depth.reshape(b, 1, h * w).float()
+    pc = torch.matmul(proj, torch.cat([cam, torch.ones(b, 1, h * w)], dim=1))
+    px = pc[:, 0:1] / (pc[:, 2:3] + 1e-10)
+    py = pc[:, 1:2] / (pc[:, 2:3] + 1e-10)
+    px = px.reshape(b, h, w, 1) / (w - 1) * 2.0 - 1.0
+    py = py.reshape(b, h, w, 1) / (h - 1) * 2.0 - 1.0
+    x = (px.reshape(-1).float() + 1.0) * (w - 1.0) / 2.0
+    y = (py.reshape(-1).float() + 1.0) * (h - 1.0) / 2.0
+    x0 = torch.floor(x).int()
+    x1 = x0 + 1
+    y0 = torch.floor(y).int()
+    y1 = y0 + 1
+    mask = ((x0 >= 0) & (x1 <= w - 1) & (y0 >= 0) & (y0 <= h - 1)).float()
+    x0, x1 = torch.clamp(x0, 0, w - 1), torch.clamp(x1, 0, w - 1)
+    y0, y1 = torch.clamp(y0, 0, h - 1), torch.clamp(y1, 0, h - 1)
+    base = (torch.arange(b) * (w * h)).reshape(-1, 1).repeat(1, h * w).reshape(-1).long()
+    flat = img.reshape(-1, c).float()
+    pa, pb = flat[base + y0.long() * w + x0.long()], flat[base + y1.long() * w + x0.long()]
+    pcc, pd = flat[base + y0.long() * w + x1.long()], flat[base + y1.long() * w + x1.long()]
+    ux, uy = x1.float() - x, y1.float() - y
+    wa, wb, wc, wd = (ux * uy).unsqueeze(1), (ux * (1.0 - uy)).unsqueeze(1), ((1.0 - ux) * uy).unsqueeze(1), ((1.0 - ux) * (1.0 - uy)).unsqueeze(1)
+    out = wa * pa + wb * pb + wc * pcc + wd * pd
+    return out.reshape(b, h, w, c), mask.reshape(b, h, w, 1)
+
+
+def cross_view_loss(inputs, imgs: torch.Tensor, sample_cams, depth_gt_ms, depth_loss_weights) -> torch.Tensor:
+    """Reference models/module.py:624-691: per stage and source view a SCALAR smooth-L1 between the source image
+    warped with the estimated and with the ground-truth depth (:618-620), broadcast over the pixels where both
+    warps are valid, + 1e4 elsewhere; per pixel the two smallest are summed (top-k, :672-680), averaged over the
+    pixels and weighted per stage."""
+    num_views = imgs.shape[1]
+    total = torch.zeros(())
+    for key in [k for k in inputs.keys() if "stage" in k]:
+        depth_est = inputs[key]["depth"].unsqueeze(1)
+        depth_gt = depth_gt_ms[key].unsqueeze(1)
+        scale = depth_est.shape[-1] / imgs.shape[-1]
+        ref_cam = sample_cams[key][:, 0]
+        losses = []
+        for v in range(1, num_views):
+            view_img = F.interpolate(imgs[:, v], scale_factor=scale, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+            view_cam = sample_cams[key][:, v]
+            w_est, m_est = inverse_warping(view_img, ref_cam, view_cam, depth_est)
+            w_gt, m_gt = inverse_warping(view_img, ref_cam, view_cam, depth_gt)
+            mask = m_est * m_gt
+            l = F.smooth_l1_loss(w_est * mask, w_gt * mask, reduction="mean")
+            losses.append(l + 1e4 * (1 - mask))
+        vol = torch.stack(losses).permute(1, 2, 3, 4, 0)
+        top_vals, _ = torch.topk(torch.neg(vol), k=2, sorted=False)
+        top_vals = torch.neg(top_vals)
+        top_vals = top_vals * (top_vals < 1e4).float()
+        stage_idx = int(key.replace("stage", "")) - 1
+        total = total + torch.mean(torch.sum(top_vals, dim=-1)) * depth_loss_weights[stage_idx]
+    return total
+
+
+# --------------------------------------------------------------------------
 # whole stage
 # --------------------------------------------------------------------------
 def depthnet_forward(stage_idx: int, features: List[torch.Tensor], proj_matrices: torch.Tensor,

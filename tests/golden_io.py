@@ -72,3 +72,15 @@ def load_fusion_filter():
     """Geometric-consistency filter fixture (tests/golden/make_golden_filter.py), numpy arrays keyed 'a/...', 'b/...'."""
     npz = np.load(os.path.join(GOLDEN, "fusion_filter.npz"))
     return {k: np.asarray(npz[k]) for k in npz.files}
+
+
+def load_cross_view_loss():
+    """Cross-view photometric loss fixture (tests/golden/make_golden_cvl.py)."""
+    npz = np.load(os.path.join(GOLDEN, "cross_view_loss.npz"))
+    out = {"imgs": torch.from_numpy(npz["imgs"]), "loss": float(npz["loss"]), "dlossw": [float(x) for x in npz["dlossw"]],
+           "cams": {}, "depth_est": {}, "depth_gt": {}, "grad": {}}
+    for s in (1, 2, 3):
+        k = f"stage{s}"
+        for f in ("cams", "depth_est", "depth_gt", "grad"):
+            out[f][k] = torch.from_numpy(npz[f"{k}/{f}"])
+    return out
