@@ -10,9 +10,9 @@ start, like DDP's initial sync.  Parameters that never receive a gradient (the d
 net) are left out of the bucket -- the reference as committed needs
 ``find_unused_parameters`` for them.
 
-The loss is the depth term of the reference's ``cas_mvsnet_loss`` (models/module.py:702-714): masked smooth-L1 per
-stage, weighted by ``dlossw`` (train.py:65 default 0.5,1.0,2.0).  The cross-view photometric term
-(models/module.py:624-691) sits outside the hot path.
+The loss is the reference's ``cas_mvsnet_loss`` (models/module.py:695-719): masked smooth-L1 depth term per stage,
+weighted by ``dlossw`` (train.py:65 default 0.5,1.0,2.0), plus -- when images and cameras are handed to
+``train_step`` -- 12 x the cross-view photometric term (``damvsnet_b200.losses.cross_view_loss``, native).
 """
 from __future__ import annotations
 
@@ -130,11 +130,19 @@ class HotPathTrainer:
         return [self.depthnet(i, f, p, d, d.shape[1], self.cost_regularization[i]) for i, (f, p, d) in enumerate(stages)]
 
     def train_step(self, stages: Sequence[StageInput], depth_gt: Sequence[torch.Tensor], masks: Sequence[torch.Tensor],
-                   dlossw: Sequence[float] = (0.5, 1.0, 2.0)) -> torch.Tensor:
-        """forward -> loss -> backward -> gradient all-reduce -> Adam step.  Returns the (local) loss tensor."""
+                   dlossw: Sequence[float] = (0.5, 1.0, 2.0), imgs: Optional[torch.Tensor] = None,
+                   sample_cams: Optional[Dict[str, torch.Tensor]] = None, cpc_weight: float = 12.0) -> torch.Tensor:
+        """forward -> loss -> backward -> gradient all-reduce -> Adam step.  Returns the (local) loss tensor.
+        With `imgs` [B,N,3,H,W] and `sample_cams` {stageK: [B,N,2,4,4]} the loss is the reference's full
+        cas_mvsnet_loss: depth term + 12 x cross-view photometric term (models/module.py:700-717)."""
         self.optimizer.zero_grad(set_to_none=False)
         outs = self.forward(stages)
         loss = depth_loss(outs, depth_gt, masks, dlossw)
+        if imgs is not None:
+            from .losses import cross_view_loss
+            named = {f"stage{i + 1}": o for i, o in enumerate(outs)}
+            gts = {f"stage{i + 1}": g for i, g in enumerate(depth_gt)}
+            loss = loss + cpc_weight * cross_view_loss(named, imgs, sample_cams, gts, list(dlossw))
         loss.backward()
         self.bucket.allreduce(self.group)
         self.optimizer.step()

@@ -211,3 +211,23 @@ def test_weight_gradient_kernels_match_torch(dm, cin, cout, stride, transposed):
         dw = ops_train.conv3d_wgrad(xv, gv, cin, cout, stride, transposed).cpu()
         assert dw.shape == w.shape
         assert rel(dw, w.grad) < tol, (dtype, rel(dw, w.grad))
+
+
+def test_trainer_step_with_full_reference_loss_decreases_loss(dm):
+    """HotPathTrainer: three stages, depth + 12 x cross-view loss (models/module.py:700-717), Adam; a few steps on one
+    fixed batch reduce the loss and keep every parameter finite."""
+    from damvsnet_b200 import synthetic
+    from damvsnet_b200.runner import make_workload
+    from damvsnet_b200.training import HotPathTrainer
+    B, N, H, W, nds = 2, 3, 64, 96, [16, 8, 8]
+    with dm.precision("bf16"):
+        tr = HotPathTrainer(synthetic.hot_path_state_dict(seed=4), device=dev(), lr=2e-3)
+        stages = make_workload(H, W, N, nds, batch=B, seed=3, device=dev())
+        stages = [([f.requires_grad_(True) for f in fs], p, d) for fs, p, d in stages]
+        gts = [d[:, d.shape[1] // 2].contiguous() for _, _, d in stages]
+        masks = [torch.ones_like(g) for g in gts]
+        imgs = synthetic.make_images(B, N, H, W, seed=1).to(dev())
+        cams = {f"stage{i + 1}": p for i, (_, p, _) in enumerate(stages)}
+        losses = [float(tr.train_step(stages, gts, masks, imgs=imgs, sample_cams=cams)) for _ in range(6)]
+    assert all(torch.isfinite(p).all() for p in tr.params)
+    assert losses[-1] < losses[0], losses
