@@ -121,19 +121,24 @@ class HotPathRunner:
     def h2d_bytes(stages: Sequence[StageInput]) -> int:
         n = 0
         for feats, proj, dv in stages:
-            n += sum(f.numel() * f.element_size() for f in feats) + proj.numel() * 4 + dv.numel() * 4
+            n += sum(f.numel() * f.element_size() for f in feats) + proj.numel() * 4 + (0 if dv is None else dv.numel() * 4)
         return n
 
     @staticmethod
     def d2h_bytes(stages: Sequence[StageInput]) -> int:
-        return sum(3 * dv.shape[0] * dv.shape[2] * dv.shape[3] * 4 for _, _, dv in stages)
+        return sum(3 * f[0].shape[0] * f[0].shape[2] * f[0].shape[3] * 4 for f, _, _ in stages)
 
     @torch.no_grad()
-    def submit_host(self, stages: Sequence[StageInput]) -> "HostTicket":
+    def submit_host(self, stages: Sequence[StageInput], cascade=None) -> "HostTicket":
         """Enqueue one view whose inputs live in (pinned) host memory: H2D on the copy stream, the three stages
         on the compute stream (stage s waits only for its own inputs), D2H of depth / confidence / variance on
         the readback stream.  Returns immediately; `collect` waits.  Submitting view i+1 before collecting
-        view i overlaps its upload with view i's kernels."""
+        view i overlaps its upload with view i's kernels.
+
+        `cascade` = (depth_range [B,Dtot] host tensor, ndepths, height, width) chains the stages as
+        CascadeMVSNet.forward does (reference models/cas_mvsnet.py:236-296): a stage whose hypotheses are `None`
+        gets them on the device -- stage 1 from the plane-sweep range, later stages from the previous stage's depth
+        and variance through the fused sampling kernel -- so only features and cameras cross PCIe."""
         dev = self.device
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
@@ -148,11 +153,12 @@ class HotPathRunner:
         # set k is overwritten only after the kernels that last read it have finished
         bset = self._submits % 2
         self._submits += 1
-        if self._dev_in[bset] is None or [[tuple(t.shape) for t in st[0]] + [tuple(st[1].shape), tuple(st[2].shape)] for st in self._dev_in[bset]] != \
-                [[tuple(f.shape) for f in feats] + [tuple(proj.shape), tuple(dv.shape)] for feats, proj, dv in stages]:
+        shp = lambda t: None if t is None else tuple(t.shape)
+        if self._dev_in[bset] is None or [[tuple(t.shape) for t in st[0]] + [tuple(st[1].shape), shp(st[2])] for st in self._dev_in[bset]] != \
+                [[tuple(f.shape) for f in feats] + [tuple(proj.shape), shp(dv)] for feats, proj, dv in stages]:
             self._dev_in[bset] = [([torch.empty(f.shape, dtype=f.dtype, device=dev) for f in feats],
                                 torch.empty(proj.shape, dtype=proj.dtype, device=dev),
-                                torch.empty(dv.shape, dtype=dv.dtype, device=dev)) for feats, proj, dv in stages]
+                                None if dv is None else torch.empty(dv.shape, dtype=dv.dtype, device=dev)) for feats, proj, dv in stages]
             self._set_done[bset] = None
         if self._set_done[bset] is not None:
             copy.wait_event(self._set_done[bset])
@@ -162,12 +168,13 @@ class HotPathRunner:
                 for src, dst in zip(feats, bfe):
                     dst.copy_(src, non_blocking=True)
                 bpr.copy_(proj, non_blocking=True)
-                bdv.copy_(dv, non_blocking=True)
+                if dv is not None:
+                    bdv.copy_(dv, non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy)
                 uploaded.append((bfe, bpr, bdv))
                 ready.append(ev)
-        shapes = [(dv.shape[0], dv.shape[2], dv.shape[3]) for _, _, dv in stages]
+        shapes = [(f[0].shape[0], f[0].shape[2], f[0].shape[3]) for f, _, _ in stages]
         host = None
         for i, cand in enumerate(self._host_pool):
             if [tuple(o["depth"].shape) for o in cand] == shapes:
@@ -176,9 +183,23 @@ class HotPathRunner:
         if host is None:
             host = [{k: torch.empty(sh, dtype=torch.float32).pin_memory()
                      for k in ("depth", "photometric_confidence", "variance")} for sh in shapes]
+        prev = None
         for i, ((dfe, dpr, ddv), ev) in enumerate(zip(uploaded, ready)):
             compute.wait_event(ev)
+            if ddv is None:
+                from . import ops
+                rng_host, ndepths, height, width = cascade
+                b, _, h, w = dfe[0].shape
+                if prev is None:          # plane-sweep range -> evenly spaced hypotheses (models/module.py:1003-1010)
+                    rng = rng_host.to(dev, non_blocking=True)
+                    lo, hi = rng[:, 0], rng[:, -1]
+                    vals = lo.unsqueeze(1) + torch.arange(ndepths[i], device=dev, dtype=torch.float32).view(1, -1) * \
+                        ((hi - lo) / (ndepths[i] - 1)).unsqueeze(1)
+                    ddv = vals.view(b, -1, 1, 1).expand(b, ndepths[i], h, w).contiguous()
+                else:
+                    ddv = ops.stage_hypotheses(prev["depth"], prev["variance"], ndepths[i], height, width, height // h)
             out = self.run_stage(i, dfe, dpr, ddv)
+            prev = out
             done = torch.cuda.Event()
             done.record(compute)
             d2h.wait_event(done)

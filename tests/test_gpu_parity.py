@@ -468,3 +468,26 @@ def test_tanks_and_temples_shape_seven_views_invariants(dm):
     span = (d3.max(1).values - d3.min(1).values).clamp_min(1e-6)
     err = ((outs[2]["depth"] - ref["depth"]).abs() / span)
     assert err.median() < 2.5e-3 and err.quantile(0.99) < 3e-2
+
+
+def test_host_cascade_pipeline_matches_device_cascade(dm):
+    """submit_host(cascade=...) -- features + cameras + plane-sweep range from pinned host memory, hypotheses of stages
+    2/3 sampled on the device -- gives what run_cascade gives on device-resident inputs."""
+    from damvsnet_b200 import synthetic
+    from damvsnet_b200.runner import HotPathRunner
+    H, W, N, nds = 64, 96, 3, [16, 8, 8]
+    sd = synthetic.hot_path_state_dict(seed=3)
+    feats = [synthetic.make_stage_inputs(s, 1, N, H, W, nds[s], seed=6)[0] for s in range(3)]
+    projs, _ = synthetic.make_cameras(1, N, H, W, seed=6)
+    dvals = synthetic.make_depth_range(1, 192)
+    runner = HotPathRunner(sd, device=dev())
+    want = runner.run_cascade([[f.to(dev()) for f in fs] for fs in feats], {k: v.to(dev()) for k, v in projs.items()},
+                              dvals.to(dev()), nds, H, W)
+    pinned = [([f.pin_memory() for f in feats[s]], projs[f"stage{s + 1}"].pin_memory(), None) for s in range(3)]
+    for _ in range(2):      # second submit reuses the device / host buffers
+        t = runner.submit_host(pinned, cascade=(dvals.pin_memory(), nds, H, W))
+        got = runner.collect(t)
+        for s in range(3):
+            for k in ("depth", "photometric_confidence", "variance"):
+                torch.testing.assert_close(got[s][k], want[f"stage{s + 1}"][k].cpu(), rtol=1e-5, atol=1e-4)
+        runner.release(t)
