@@ -49,6 +49,8 @@ _SIGNATURES = {
     "damvs_bn_stats": (c_int, [c_void_p] + [c_int] * 6 + [c_void_p, c_void_p]),
     "damvs_bn_apply": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     "damvs_bn_bwd": (c_int, [c_void_p] * 9 + [c_int] * 7 + [c_void_p]),
+    "damvs_bn_finalize": (c_int, [c_void_p] * 5 + [c_double, c_float, c_float] + [c_void_p] * 4 + [c_int, c_void_p]),
+    "damvs_bn_bwd_coeffs": (c_int, [c_void_p] * 4 + [c_double] + [c_void_p] * 5 + [c_int, c_void_p]),
     "damvs_plain_to_g8": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p]),
     "damvs_conv3d_wgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p]),
     "damvs_warp_agg_bwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p,

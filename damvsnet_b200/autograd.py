@@ -28,21 +28,24 @@ from .ops import G8Volume
 # --------------------------------------------------------------------------
 # BatchNorm coefficient algebra (C-sized, host side of damvs_bn_*)
 # --------------------------------------------------------------------------
-def _batch_stats(bn: torch.nn.BatchNorm3d, y: torch.Tensor):
-    """Batch mean / rstd of a G8 volume and the running-buffer update of nn.BatchNorm3d.forward in training."""
+def _batch_norm_coeffs(bn: torch.nn.BatchNorm3d, y: torch.Tensor, gamma, beta):
+    """Batch statistics of a G8 volume -> (scale, shift, mean, rstd), with the running-buffer update of
+    nn.BatchNorm3d.forward in training mode; two launches (damvs_bn_stats, damvs_bn_finalize)."""
     c = y.shape[1] * 8
     m = y.numel() // c
     sums = ops_train.bn_stats(y)
-    mean = sums[:, 0] / m
-    var = (sums[:, 1] / m - mean * mean).clamp_min(0.0)
-    with torch.no_grad():
-        if bn.track_running_stats and bn.running_mean is not None:
+    track = bn.track_running_stats and bn.running_mean is not None
+    f = 0.0
+    if track:
+        with torch.no_grad():
             bn.num_batches_tracked += 1
-            f = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else bn.momentum
-            bn.running_mean.mul_(1 - f).add_(mean.to(bn.running_mean.dtype), alpha=f)
-            bn.running_var.mul_(1 - f).add_((var * (m / max(m - 1, 1))).to(bn.running_var.dtype), alpha=f)
-    rstd = torch.rsqrt(var + bn.eps)
-    return mean.float(), rstd.float()
+        # momentum None = cumulative average; needs the counter's value (a host read, as in nn.BatchNorm itself)
+        f = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else bn.momentum
+    g = None if gamma is None else gamma.detach().float()
+    b = None if beta is None else beta.detach().float()
+    rm = bn.running_mean if track and bn.running_mean.dtype == torch.float32 else None
+    rv = bn.running_var if rm is not None else None
+    return ops_train.bn_finalize(sums, g, b, rm, rv, m, f, bn.eps)
 
 
 class ConvBlockFn(torch.autograd.Function):
@@ -57,11 +60,10 @@ class ConvBlockFn(torch.autograd.Function):
                        impl).data
         bn = blk.bn
         batch = bn is not None and (blk.training or not bn.track_running_stats)
-        if bn is not None:
-            if batch:
-                mean, rstd = _batch_stats(bn, y)
-            else:
-                mean, rstd = bn.running_mean.float(), torch.rsqrt(bn.running_var.float() + bn.eps)
+        if bn is not None and batch:
+            scale, shift, mean, rstd = _batch_norm_coeffs(bn, y, gamma, beta)
+        elif bn is not None:
+            mean, rstd = bn.running_mean.float(), torch.rsqrt(bn.running_var.float() + bn.eps)
             g = gamma.detach().float() if gamma is not None else torch.ones_like(mean)
             scale = g * rstd
             shift = (beta.detach().float() if beta is not None else torch.zeros_like(mean)) - mean * scale
@@ -84,18 +86,11 @@ class ConvBlockFn(torch.autograd.Function):
         m = y.numel() // cout
         if ctx.batch:
             _, sums = ops_train.bn_bwd(g_out, y, scale, shift, None, None, None, blk.relu, False, True)
-            sg, sgy = sums[:, 0], sums[:, 1]
-            mean64, rstd64 = mean.double(), rstd.double()
-            dot = rstd64 * (sgy - mean64 * sg)                   # sum g_z * yhat  (= d gamma)
-            m1, m2 = sg / m, dot / m
-            k1 = scale.double()
-            k2 = -k1 * rstd64 * m2
-            k3 = k1 * (mean64 * rstd64 * m2 - m1)
-            g_y, _ = ops_train.bn_bwd(g_out, y, scale, shift, k1.float(), k2.float(), k3.float(), blk.relu, True, False)
+            k1, k2, k3, dgamma, dbeta = ops_train.bn_bwd_coeffs(sums, scale, mean, rstd, m, True)
+            g_y, _ = ops_train.bn_bwd(g_out, y, scale, shift, k1, k2, k3, blk.relu, True, False)
         else:
             g_y, sums = ops_train.bn_bwd(g_out, y, scale, shift, scale, None, None, blk.relu, True, True)
-            sg, sgy = sums[:, 0], sums[:, 1]
-            dot = rstd.double() * (sgy - mean.double() * sg)
+            _, _, _, dgamma, dbeta = ops_train.bn_bwd_coeffs(sums, scale, mean, rstd, m, False)
         g_x = g_w = g_gamma = g_beta = None
         if ctx.needs_input_grad[0]:
             a_stride, a_tr = (1, False) if (stride == 1 and not tr) else ((2, False) if tr else (2, True))
@@ -106,9 +101,9 @@ class ConvBlockFn(torch.autograd.Function):
             g_w = ops_train.conv3d_wgrad(x, g_y, cin, cout, stride, tr)
         if blk.bn is not None:
             if ctx.needs_input_grad[3]:
-                g_gamma = dot.float()
+                g_gamma = dgamma
             if ctx.needs_input_grad[4]:
-                g_beta = sg.float()
+                g_beta = dbeta
         g_skip = g_out if (ctx.has_skip and ctx.needs_input_grad[1]) else None
         return g_x, g_skip, g_w, g_gamma, g_beta, None
 

@@ -9,8 +9,8 @@
 //   bn_apply_kernel    out = skip + act(y * scale[c] + shift[c])
 //   bn_bwd_kernel      g_z = g_out * [act active];  sums[c] += {sum g_z, sum g_z*y};
 //                      g_y = k1[c] * g_z + k2[c] * y + k3[c]
-// The per-channel coefficient algebra (mean/var -> scale/shift, the BatchNorm backward formula -> k1,k2,k3,
-// d gamma, d beta, running-statistics update) is C-sized and stays on the host side (damvsnet_b200/autograd.py).
+//   bn_finalize_kernel / bn_bwd_coeffs_kernel   the C-sized coefficient algebra between them (mean/var -> scale/shift
+//                      and running buffers; BatchNorm backward formula -> k1,k2,k3, d gamma, d beta), one launch each.
 #include "common.cuh"
 
 namespace damvs {
@@ -147,6 +147,50 @@ __global__ void __launch_bounds__(256) plain_to_g8_kernel(const float* __restric
   store8(out + i * 8, r);
 }
 
+// C-sized coefficient algebra of a training-mode BatchNorm, one thread per channel (replaces ~12 tiny tensor ops per block).
+// Forward: batch mean / biased variance from the fp64 sums, running-buffer update (momentum, unbiased variance), and the
+// folded affine scale = gamma * rstd, shift = beta - mean * scale.
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var, double count, float momentum, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[2 * c] / count;
+  double var = sums[2 * c + 1] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  if (running_mean) {
+    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * var * (count / fmax(count - 1.0, 1.0)));
+  }
+  const double rstd = rsqrt(var + (double)eps);
+  const double g = gamma ? (double)gamma[c] : 1.0, b = beta ? (double)beta[c] : 0.0;
+  const double sc = g * rstd;
+  scale[c] = (float)sc;
+  shift[c] = (float)(b - mean * sc);
+  mean_out[c] = (float)mean;
+  rstd_out[c] = (float)rstd;
+}
+
+// Backward: from sums = {sum g_z, sum g_z * y}:  d gamma = rstd (sum g_z y - mean sum g_z),  d beta = sum g_z, and (batch
+// statistics only) the coefficients of g_y = k1 g_z + k2 y + k3 = scale (g_z - mean(g_z) - yhat mean(g_z yhat)).
+__global__ void bn_bwd_coeffs_kernel(const double* __restrict__ sums, const float* __restrict__ scale, const float* __restrict__ mean,
+                                     const float* __restrict__ rstd, double count, float* __restrict__ k1, float* __restrict__ k2,
+                                     float* __restrict__ k3, float* __restrict__ g_gamma, float* __restrict__ g_beta, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double sg = sums[2 * c], sgy = sums[2 * c + 1], mu = mean[c], rs = rstd[c], sc = scale[c];
+  const double dot = rs * (sgy - mu * sg);
+  if (g_gamma) g_gamma[c] = (float)dot;
+  if (g_beta) g_beta[c] = (float)sg;
+  if (k1) {
+    const double m1 = sg / count, m2 = dot / count;
+    k1[c] = (float)sc;
+    k2[c] = (float)(-sc * rs * m2);
+    k3[c] = (float)(sc * (mu * rs * m2 - m1));
+  }
+}
+
 static bool vol_args_ok(int B, int C, int D, int H, int W) {
   return B > 0 && C > 0 && C % 8 == 0 && D > 0 && H > 0 && W > 0 && (long long)B * (C / 8) <= 65535;
 }
@@ -206,6 +250,26 @@ extern "C" int damvs_bn_bwd(const void* g_out, const void* y, const float* scale
                                                       (__nv_bfloat16*)g_y, sums, G, V, relu);
   else return set_error(DAMVS_ERR_INVALID, "bn_bwd: bad dtype %d", dtype);
   DAMVS_LAUNCH_OK("bn_bwd kernel");
+  return DAMVS_OK;
+}
+
+extern "C" int damvs_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                 double count, float momentum, float eps, float* scale, float* shift, float* mean, float* rstd, int C,
+                                 void* stream) {
+  DAMVS_REQUIRE(sums && scale && shift && mean && rstd && C > 0 && count > 0, "bn_finalize: bad arguments");
+  DAMVS_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bn_finalize: running buffers come in pairs");
+  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sums, gamma, beta, running_mean, running_var, count, momentum, eps, scale,
+                                                                   shift, mean, rstd, C);
+  DAMVS_LAUNCH_OK("bn_finalize kernel");
+  return DAMVS_OK;
+}
+
+extern "C" int damvs_bn_bwd_coeffs(const double* sums, const float* scale, const float* mean, const float* rstd, double count, float* k1,
+                                   float* k2, float* k3, float* g_gamma, float* g_beta, int C, void* stream) {
+  DAMVS_REQUIRE(sums && scale && mean && rstd && C > 0 && count > 0, "bn_bwd_coeffs: bad arguments");
+  DAMVS_REQUIRE((k1 == nullptr) == (k2 == nullptr) && (k1 == nullptr) == (k3 == nullptr), "bn_bwd_coeffs: k1, k2, k3 come together");
+  bn_bwd_coeffs_kernel<<<(C + 63) / 64, 64, 0, (cudaStream_t)stream>>>(sums, scale, mean, rstd, count, k1, k2, k3, g_gamma, g_beta, C);
+  DAMVS_LAUNCH_OK("bn_bwd_coeffs kernel");
   return DAMVS_OK;
 }
 

@@ -71,6 +71,32 @@ def bn_bwd(g_out: torch.Tensor, y: torch.Tensor, scale, shift, k1, k2, k3, relu:
     return g_y, sums
 
 
+def bn_finalize(sums: torch.Tensor, gamma, beta, running_mean, running_var, count: int, momentum: float, eps: float):
+    """sums fp64 [C,2] -> (scale, shift, mean, rstd) fp32 [C]; running buffers (or None) updated in place."""
+    c = sums.shape[0]
+    dev = sums.device
+    scale, shift, mean, rstd = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(4))
+    with torch.cuda.device_of(sums):
+        _lib.check(_lib.load().damvs_bn_finalize(_p(sums), _p(_f32c(gamma, c, "gamma")), _p(_f32c(beta, c, "beta")), _p(running_mean),
+                                                 _p(running_var), float(count), float(momentum), float(eps), _p(scale), _p(shift),
+                                                 _p(mean), _p(rstd), c, _stream()))
+    return scale, shift, mean, rstd
+
+
+def bn_bwd_coeffs(sums: torch.Tensor, scale, mean, rstd, count: int, batch_stats: bool):
+    """sums fp64 [C,2] -> (k1, k2, k3 | None x3, g_gamma, g_beta) fp32 [C]."""
+    c = sums.shape[0]
+    dev = sums.device
+    g_gamma, g_beta = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(2))
+    k1 = k2 = k3 = None
+    if batch_stats:
+        k1, k2, k3 = (torch.empty(c, dtype=torch.float32, device=dev) for _ in range(3))
+    with torch.cuda.device_of(sums):
+        _lib.check(_lib.load().damvs_bn_bwd_coeffs(_p(sums), _p(scale), _p(mean), _p(rstd), float(count), _p(k1), _p(k2), _p(k3),
+                                                   _p(g_gamma), _p(g_beta), c, _stream()))
+    return k1, k2, k3, g_gamma, g_beta
+
+
 def plain_to_g8(t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """[B,D,H,W] fp32 -> G8 volume [B,1,D,H,W,8] (channel 0 = value, the rest zero)."""
     if t.dtype != torch.float32 or t.dim() != 4 or not t.is_cuda:

@@ -179,6 +179,18 @@ int damvs_bn_bwd(const void* g_out, const void* y, const float* scale, const flo
                  const float* k3, void* g_y, double* sums, int dtype, int B, int C, int D, int H, int W, int relu,
                  void* stream);
 
+/* The C-sized coefficient algebra between those kernels, one launch each (device pointers, [C] fp32 unless noted).
+ * finalize: sums (fp64 [C][2] from damvs_bn_stats over `count` voxels) -> batch mean / rstd, scale = gamma * rstd,
+ *   shift = beta - mean * scale; running_mean / running_var (NULL to skip) are updated in place with `momentum` and
+ *   the unbiased variance, as nn.BatchNorm3d.forward does in training.
+ * bwd_coeffs: sums (fp64 [C][2] from damvs_bn_bwd) -> g_gamma, g_beta and, for batch statistics, k1, k2, k3 of
+ *   damvs_bn_bwd's second call (NULL for fixed statistics).                                                     */
+int damvs_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      double count, float momentum, float eps, float* scale, float* shift, float* mean, float* rstd, int C,
+                      void* stream);
+int damvs_bn_bwd_coeffs(const double* sums, const float* scale, const float* mean, const float* rstd, double count, float* k1,
+                        float* k2, float* k3, float* g_gamma, float* g_beta, int C, void* stream);
+
 /* [voxels] fp32 -> G8 volume of one channel group: channel 0 = value, channels 1..7 = 0 (gradient of the
  * single-channel `prob` convolution's output, fed to the adjoint convolution and to damvs_conv3d_wgrad). */
 int damvs_plain_to_g8(const float* in, void* out, int dtype, long long voxels, void* stream);
