@@ -627,15 +627,22 @@ size_t conv3d_tc_packed_bytes(const damvs_conv3d_desc* d) {
 
 // B operand of step s: [2 K-halves][N = 3*CP rows][8 channels] bf16; row n = j*CP + co where j is the folded
 // w tap (conv: kw = j; transposed: tw = {1, 2, 0}[j]).
-__global__ void pack_weight_tc_kernel(const float* __restrict__ w, uint8_t* __restrict__ blob, int Cin, int Cout, int co_end,
-                                      int transposed, int CP, int n0, int nsteps) {
-  const StepSrc* steps = reinterpret_cast<const StepSrc*>(blob + steps_offset());
+// The header and the step table travel as a by-value kernel argument and are written by the kernel itself: packing is
+// fully asynchronous (no staging copy, no stream synchronisation), so it can run every training step and inside graphs.
+struct PackMeta {
+  PackedHeader hdr;
+  StepSrc steps[kMaxSteps];
+};
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, uint8_t* __restrict__ blob, const __grid_constant__ PackMeta meta, int Cin,
+                                      int Cout, int co_end, int transposed, int CP, int n0, int nsteps) {
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(blob + weights_offset(nsteps));
   const int N = 3 * CP;
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [nsteps][2][N][8]
+  if (i == 0) *reinterpret_cast<PackedHeader*>(blob) = meta.hdr;
+  if (i < nsteps) reinterpret_cast<StepSrc*>(blob + steps_offset())[i] = meta.steps[i];
   if (i >= nsteps * 2 * N * 8) return;
   int j8 = i & 7, n = (i >> 3) % N, h = (i / (8 * N)) & 1, s = i / (16 * N);
-  StepSrc st = steps[s];
+  StepSrc st = meta.steps[s];
   const int jw = n / CP, col = n - jw * CP;
   const int kw = transposed ? (jw == 0 ? 1 : (jw == 1 ? 2 : 0)) : jw;
   int co = n0 + col, ci = st.g[h] * 8 + j8, tap2 = st.tap[h];
@@ -660,19 +667,17 @@ int conv3d_tc_pack(const damvs_conv3d_desc* d, const float* weight, void* packed
   const size_t bb = (blob_bytes(nsteps, CP) + 255) / 256 * 256;
   for (int k = 0; k < split; ++k) {
     uint8_t* blob = (uint8_t*)packed + k * bb;
-    PackedHeader h{};
+    PackMeta meta{};
+    PackedHeader& h = meta.hdr;
     h.magic = kMagic; h.mode = mode; h.Cin = d->Cin; h.Cout = d->Cout; h.CP = CP; h.nsteps = nsteps;
     h.ncls = mode == MODE_T ? 4 : 1; h.n0 = k * cper; h.blob_bytes = (int)bb; h.nblobs = split;
-    DAMVS_CUDA_OK(cudaMemcpyAsync(blob, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-    DAMVS_CUDA_OK(cudaMemcpyAsync(blob + steps_offset(), steps.data(), nsteps * sizeof(StepSrc), cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < nsteps; ++i) meta.steps[i] = steps[i];
     int total = nsteps * 2 * 3 * CP * 8;
     // the blob computes channels [n0, n0 + cper); rows beyond that are zero padding
-    pack_weight_tc_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, blob, d->Cin, d->Cout, (k + 1) * cper, d->transposed, CP,
+    pack_weight_tc_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, blob, meta, d->Cin, d->Cout, (k + 1) * cper, d->transposed, CP,
                                                               k * cper, nsteps);
     DAMVS_LAUNCH_OK("pack_weight_tc kernel");
   }
-  // the host staging buffers above are read by the async copies: make them safe to drop
-  DAMVS_CUDA_OK(cudaStreamSynchronize(st));
   return DAMVS_OK;
 }
 

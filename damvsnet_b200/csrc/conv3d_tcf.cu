@@ -300,10 +300,12 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
 }
 
 // B operand of step st: [2 K-halves][N3 rows][8 channels] bf16; row n = j * 48 + kw * 16 + co with j = 2 - kd.
-__global__ void pack_weight_tcf_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cin, int Cout, int G, int nsteps,
-                                       int CP, int NB) {
+__global__ void pack_weight_tcf_kernel(const float* __restrict__ w, uint8_t* __restrict__ blob, const __grid_constant__ Header hdr, int Cin, int Cout,
+                                       int G, int nsteps, int CP, int NB) {
   const int N3 = 3 * NB;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(blob + sizeof(Header));
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [nsteps][2][N3][8]
+  if (i == 0) *reinterpret_cast<Header*>(blob) = hdr;     // by-value argument: no staging copy, no synchronisation
   if (i >= nsteps * 2 * N3 * 8) return;
   const int j8 = i & 7, n = (i >> 3) % N3, hh = (i / (8 * N3)) & 1, st = i / (16 * N3);
   const int kd = 2 - n / NB, kw = (n % NB) / CP, co = (n % NB) % CP;
@@ -390,12 +392,9 @@ int conv3d_tcf_pack(const damvs_conv3d_desc* d, const float* weight, void* packe
   tcf::Header h{};
   const int cpn = tcf::cpn_of(d), nb = cpn == 8 ? tcf::Shape<8>::NB : tcf::Shape<16>::NB;
   h.magic = tcf::kMagicF; h.Cin = d->Cin; h.Cout = d->Cout; h.nsteps = nsteps; h.pad[0] = cpn;
-  DAMVS_CUDA_OK(cudaMemcpyAsync(packed, &h, sizeof(h), cudaMemcpyHostToDevice, st));
   const int total = nsteps * 2 * 3 * nb * 8;
-  tcf::pack_weight_tcf_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, reinterpret_cast<__nv_bfloat16*>((uint8_t*)packed + sizeof(tcf::Header)),
-                                                                  d->Cin, d->plain_out ? 1 : d->Cout, G, nsteps, cpn, nb);
+  tcf::pack_weight_tcf_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, (uint8_t*)packed, h, d->Cin, d->plain_out ? 1 : d->Cout, G, nsteps, cpn, nb);
   DAMVS_LAUNCH_OK("pack_weight_tcf kernel");
-  DAMVS_CUDA_OK(cudaStreamSynchronize(st));   // the header staging buffer is on this stack frame
   return DAMVS_OK;
 }
 

@@ -371,17 +371,8 @@ template <int C, int MODE>
 static int launch_warp_agg(const WarpAggParams& P, int out_dtype, cudaStream_t st) {
   constexpr int TW = 32 / (C / 8), TH = 4, DCH = 4;
   dim3 grid((P.W + TW - 1) / TW, (P.H + TH - 1) / TH, P.B);
-  static const int cfg = getenv("DAMVS_WARP_CFG") ? atoi(getenv("DAMVS_WARP_CFG")) : 0;   // development knob
   if (out_dtype == DAMVS_F32)
     warp_agg_kernel<C, MODE, float, DCH, false><<<grid, 128, 0, st>>>(P);
-  else if (cfg == 1)
-    warp_agg_kernel<C, MODE, __nv_bfloat16, 4, true><<<grid, 128, 0, st>>>(P);
-  else if (cfg == 2)
-    warp_agg_kernel<C, MODE, __nv_bfloat16, 2, false><<<grid, 128, 0, st>>>(P);
-  else if (cfg == 3)
-    warp_agg_kernel<C, MODE, __nv_bfloat16, 2, true><<<grid, 128, 0, st>>>(P);
-  else if (cfg == 4)
-    warp_agg_kernel<C, MODE, __nv_bfloat16, 8, false><<<grid, 128, 0, st>>>(P);
   else
     warp_agg_kernel<C, MODE, __nv_bfloat16, DCH, false><<<grid, 128, 0, st>>>(P);
   DAMVS_LAUNCH_OK("warp_agg kernel");
