@@ -491,3 +491,27 @@ def test_host_cascade_pipeline_matches_device_cascade(dm):
             for k in ("depth", "photometric_confidence", "variance"):
                 torch.testing.assert_close(got[s][k], want[f"stage{s + 1}"][k].cpu(), rtol=1e-5, atol=1e-4)
         runner.release(t)
+
+
+@pytest.mark.parametrize("mode", ["adaptive", "variance"])
+def test_cost_volume_edge_cases_single_source_and_out_of_view(dm, mode):
+    """N = 2 (one source view) and a source camera that looks away from the scene (every tap out of range: the warped
+    feature is zero padding everywhere, so adaptive = (w + 1) * ref^2 and variance = E[x^2] - E[x]^2 with x_src = 0),
+    on both feature paths, smallest legal image (8 x 8)."""
+    from damvsnet_b200 import synthetic
+    sd = synthetic.hot_path_state_dict(seed=11)
+    for (H, W) in ((8 * 4, 8 * 4), (4 * 21, 4 * 33)):
+        feats, pm, dv = synthetic.make_stage_inputs(0, 1, 2, H, W, 4, seed=8)
+        net, _ = _build_net(dm, sd, 0, mode)
+        pm_away = pm.clone()
+        pm_away[:, 1, 0, :3, 3] = torch.tensor([1e6, -1e6, 0.0])             # translate the source camera far away
+        for proj in (pm, pm_away):
+            want = O.aggregate(feats, proj, dv, mode, sd, 0)
+            for dt, tol in ((torch.float32, 2e-3), (torch.bfloat16, 2e-2)):
+                got = net.cost_volume(0, [f.to(dev()) for f in feats], proj.to(dev()), dv.to(dev()), out_dtype=dt).to_ncdhw().cpu()
+                scale = max(want.abs().mean().item(), 1.0)
+                assert ((got - want).abs() <= tol * (want.abs() + scale)).all(), (H, W, dt)
+        if mode == "variance":
+            away = O.aggregate(feats, pm_away, dv, mode, sd, 0)
+            ref = feats[0].unsqueeze(2).expand_as(away)
+            torch.testing.assert_close(away, ref ** 2 / 2 - (ref / 2) ** 2, rtol=1e-5, atol=1e-6)
