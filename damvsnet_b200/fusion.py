@@ -68,3 +68,38 @@ def backproject_valid(depth: torch.Tensor, mask: torch.Tensor, K, E) -> torch.Te
     cam = Ki @ pix
     world = Ei[:3, :3] @ cam + Ei[:3, 3:4]
     return world.t().float()
+
+
+def fuse_views(depths: Sequence[torch.Tensor], confidences: Sequence[Sequence[torch.Tensor]], images: Sequence[torch.Tensor],
+               Ks, Es, pairs: Sequence[tuple], conf_thr: Sequence[float] = (0.1, 0.15, 0.9), dist_base: float = 1 / 4,
+               rel_diff_base: float = 1 / 1300):
+    """The loop of reference filter/dypcd.py:filter_depth (:190-300) over a scan that is already on the GPU: for every
+    (ref_view, src_views) of `pairs` the fused filter, then the world-space points of the final mask with the reference
+    image's colours.  depths[v] [H,W], confidences[v] = (stage1, stage2, stage3) maps, images[v] [H,W,3] in [0,1].
+    Returns (xyz [n,3] fp32, rgb [n,3] uint8) on the device, in the reference's order (views, then row-major pixels)."""
+    xyz, rgb = [], []
+    for ref, srcs in pairs:
+        out = filter_reference_view(depths[ref], confidences[ref], Ks[ref], Es[ref], [depths[s] for s in srcs],
+                                    [Ks[s] for s in srcs], [Es[s] for s in srcs], conf_thr, dist_base, rel_diff_base)
+        m = out["final_mask"]
+        xyz.append(backproject_valid(out["depth_est_averaged"], m, Ks[ref], Es[ref]))
+        rgb.append((images[ref][m] * 255).to(torch.uint8))                       # filter/dypcd.py:299
+    return torch.cat(xyz, 0), torch.cat(rgb, 0)
+
+
+def write_ply(path: str, xyz, rgb) -> None:
+    """Binary little-endian PLY with the vertex layout the reference writes through plyfile (filter/dypcd.py:308-321):
+    x, y, z float32 and red, green, blue uint8."""
+    xyz = np.ascontiguousarray(xyz.detach().cpu().numpy() if isinstance(xyz, torch.Tensor) else xyz, dtype="<f4")
+    rgb = np.ascontiguousarray(rgb.detach().cpu().numpy() if isinstance(rgb, torch.Tensor) else rgb, dtype=np.uint8)
+    assert xyz.ndim == 2 and xyz.shape[1] == 3 and rgb.shape == xyz.shape
+    vert = np.empty(len(xyz), dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")])
+    for i, k in enumerate(("x", "y", "z")):
+        vert[k] = xyz[:, i]
+    for i, k in enumerate(("red", "green", "blue")):
+        vert[k] = rgb[:, i]
+    header = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\n"
+              "property uchar red\nproperty uchar green\nproperty uchar blue\nend_header\n" % len(xyz))
+    with open(path, "wb") as f:
+        f.write(header.encode("ascii"))
+        f.write(vert.tobytes())

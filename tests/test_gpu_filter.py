@@ -58,3 +58,38 @@ def test_backproject_valid_points():
     xyz = np.matmul(np.linalg.inv(K[1]), np.vstack((xs, ys, np.ones_like(xs))) * d[1][ys, xs])
     world = np.matmul(np.linalg.inv(E[1]), np.vstack((xyz, np.ones_like(xs))))[:3].T          # filter/dypcd.py:294-298
     np.testing.assert_allclose(pts, world, rtol=1e-5, atol=1e-3)
+
+
+def test_fuse_views_and_ply_round_trip(tmp_path):
+    """A three-view scan fused on the GPU: the points of every reference view equal the reference's back-projection of
+    the oracle's averaged depth under the oracle's final mask, and the PLY file parses back to the same vertices."""
+    from damvsnet_b200 import fusion
+    fx = load_fusion_filter()
+    K, E, d, c = fx["a/K"][:3], fx["a/E"][:3], fx["a/depths"][:3], fx["a/confs"]
+    rs = np.random.RandomState(5)
+    imgs = [rs.rand(*d[0].shape, 3).astype(np.float32) for _ in range(3)]
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev())
+    pairs = [(0, [1, 2]), (1, [0, 2]), (2, [1, 0])]
+    xyz, rgb = fusion.fuse_views([t(x) for x in d], [[t(x) for x in c]] * 3, [t(x) for x in imgs], list(K), list(E), pairs)
+    want_xyz, want_rgb = [], []
+    for ref, srcs in pairs:
+        o = O.filter_reference_view(d[ref], list(c), K[ref], E[ref], [d[s] for s in srcs], [K[s] for s in srcs], [E[s] for s in srcs])
+        ys, xs = np.nonzero(o["final_mask"])
+        dep = o["depth_est_averaged"][ys, xs]
+        cam = np.matmul(np.linalg.inv(K[ref]), np.vstack((xs, ys, np.ones_like(xs))) * dep)
+        want_xyz.append(np.matmul(np.linalg.inv(E[ref]), np.vstack((cam, np.ones_like(xs))))[:3].T)
+        want_rgb.append((imgs[ref][o["final_mask"]] * 255).astype(np.uint8))
+    want_xyz, want_rgb = np.concatenate(want_xyz), np.concatenate(want_rgb)
+    assert abs(len(xyz) - len(want_xyz)) <= 3                      # knife-edge pixels of the masks
+    if len(xyz) == len(want_xyz):
+        np.testing.assert_allclose(xyz.cpu().numpy(), want_xyz, rtol=1e-5, atol=2e-2)
+        assert (rgb.cpu().numpy() == want_rgb).mean() > 0.999
+    path = str(tmp_path / "scan.ply")
+    fusion.write_ply(path, xyz, rgb)
+    raw = open(path, "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    assert b"element vertex %d" % len(xyz) in head and b"property uchar blue" in head
+    vert = np.frombuffer(body, dtype=[("x", "<f4"), ("y", "<f4"), ("z", "<f4"), ("red", "u1"), ("green", "u1"), ("blue", "u1")])
+    assert len(vert) == len(xyz)
+    np.testing.assert_array_equal(vert["z"], xyz[:, 2].cpu().numpy())
+    np.testing.assert_array_equal(vert["green"], rgb[:, 1].cpu().numpy())
