@@ -217,5 +217,41 @@ class WarpWeightedFn(torch.autograd.Function):
         return (g_wt, None, None, None, g_ref, *g_srcs)
 
 
+class WarpAdaptiveTrainFn(torch.autograd.Function):
+    """The adaptive aggregation with the weight net in training mode as ONE node: score -> scalar chain -> weighted in
+    the forward; in the backward d loss / d wt (no scatter), the chain's own backward on the scalar volumes, then a
+    single scatter pass that carries both paths into the features (through the aggregate and through the score).
+    `wn` is the AggWeightNetVolume module (its BatchNorm buffers are updated once, in the forward)."""
+
+    @staticmethod
+    def forward(ctx, w1, g1, b1, w2, g2, b2, rot_trans, depth_values, out_dtype, wn, ref, *srcs):
+        srcs = list(srcs)
+        s_vol = ops_train.warp_score_fwd(ref, srcs, rot_trans, depth_values, w1.detach().reshape(-1).float())
+        with torch.enable_grad():
+            s_leaf = s_vol.detach().requires_grad_(True)
+            wt_vol = wn.score_to_weight(s_leaf)       # uses g1, b1, w2, g2, b2 (the module's own parameters)
+        vol = ops_train.warp_weighted_fwd(ref, srcs, rot_trans, depth_values, wt_vol.detach(), out_dtype)
+        ctx.chain = (s_leaf, wt_vol, (g1, b1, w2, g2, b2))
+        ctx.save_for_backward(w1, rot_trans, depth_values, ref, *srcs)
+        return vol
+
+    @staticmethod
+    def backward(ctx, g_vol):
+        w1, rot_trans, dv, ref, *srcs = ctx.saved_tensors
+        s_leaf, wt_vol, chain_params = ctx.chain
+        g_wt = ops_train.warp_gwt(ref, srcs, rot_trans, dv, g_vol)
+        wanted = [s_leaf] + [p for p in chain_params if p.requires_grad]
+        grads = torch.autograd.grad(wt_vol, wanted, g_wt, allow_unused=True)
+        g_s = grads[0] if grads[0] is not None else torch.zeros_like(s_leaf)
+        it = iter(grads[1:])
+        g_chain = [next(it) if p.requires_grad else None for p in chain_params]
+        g_ref = torch.zeros_like(ref)
+        g_srcs = [torch.zeros_like(s) for s in srcs]
+        g_w1 = ops_train.warp_merged_bwd(ref, srcs, rot_trans, dv, w1.detach().reshape(-1).float(), wt_vol.detach(), g_s, g_vol,
+                                         g_ref, g_srcs)
+        ctx.chain = None
+        return (g_w1.view_as(w1), *g_chain, None, None, None, None, g_ref, *g_srcs)
+
+
 def wants_grad(*tensors: Optional[torch.Tensor]) -> bool:
     return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)

@@ -52,10 +52,9 @@ class DepthNet(nn.Module):
                 dv = depth_values.detach().contiguous()
             nhwc = [ag.NhwcFn.apply(f) for f in features]
             if batch_stats:
-                w1 = wn.w_net[0].conv.weight.reshape(-1)
-                s_vol = ag.WarpScoreFn.apply(w1, rot_trans, dv, *nhwc)
-                wt_vol = wn.score_to_weight(s_vol)
-                return ops.G8Volume(ag.WarpWeightedFn.apply(wt_vol, rot_trans, dv, out_dtype, *nhwc))
+                a, b2 = wn.w_net[0], wn.w_net[1]
+                return ops.G8Volume(ag.WarpAdaptiveTrainFn.apply(a.conv.weight, a.bn.weight, a.bn.bias, b2.conv.weight, b2.bn.weight,
+                                                                 b2.bn.bias, rot_trans, dv, out_dtype, wn, *nhwc))
             wnet = wn.folded_with_grad() if wn is not None else None
             return ops.G8Volume(ag.WarpAggFn.apply(wnet, rot_trans, dv, self.mode, out_dtype, *nhwc))
         # bf16 pipeline: fp16 NHWC features (half the gather bytes); fp32 pipeline: exact fp32 features

@@ -14,7 +14,7 @@
 
 namespace damvs {
 
-enum { OP_SCORE_FWD = 0, OP_WEIGHTED_FWD = 1, OP_SCORE_BWD = 2, OP_WEIGHTED_BWD = 3 };
+enum { OP_SCORE_FWD = 0, OP_WEIGHTED_FWD = 1, OP_SCORE_BWD = 2, OP_WEIGHTED_BWD = 3, OP_GWT = 4, OP_MERGED_BWD = 5 };
 
 struct WarpTrainParams {
   const float* ref;
@@ -24,7 +24,7 @@ struct WarpTrainParams {
   const float* hyp;
   const float* w1;       // [C]                       (score ops)
   const float* wt_vol;   // [n_src][B][D][H][W]       (weighted ops)
-  float* s_vol;          // score fwd: out; score bwd: g_s in; weighted bwd: g_wt out
+  float* s_vol;          // score fwd: out; score bwd: g_s in; weighted bwd / gwt: g_wt out; merged bwd: g_s in
   void* vol;             // weighted fwd: out (G8); weighted bwd: g_vol in (G8)
   float* g_ref;          // accumulated
   float* g_w1;           // accumulated [C]
@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
   const int b = blockIdx.z, H = P.H, W = P.W, D = P.D, n_src = P.n_src;
   for (int i = threadIdx.x; i < n_src * 12; i += blockDim.x) s_rt[i] = P.rot_trans[((long long)(i / 12) * P.B + b) * 12 + i % 12];
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    s_w1[i] = (OP == OP_SCORE_FWD || OP == OP_SCORE_BWD) ? P.w1[i] : 0.f;
+    s_w1[i] = (OP == OP_SCORE_FWD || OP == OP_SCORE_BWD || OP == OP_MERGED_BWD) ? P.w1[i] : 0.f;
     s_gw[i] = 0.f;
   }
   __syncthreads();
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j] = 0.f; gv.v[j] = 0.f; }
-    if (OP == OP_WEIGHTED_BWD) gv = load8(vol + d * vol_stride);
+    if (OP == OP_WEIGHTED_BWD || OP == OP_GWT || OP == OP_MERGED_BWD) gv = load8(vol + d * vol_stride);
     for (int v = 0; v < n_src; ++v) {
       float ix, iy, w[4], wv[8], df[8], e[8];
       project_b(s_rt + v * 12, fx, fy, dep, inv_half_w, inv_half_h, fw, fh, ix, iy);
@@ -92,6 +92,14 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
         const float wt1 = __ldg(P.wt_vol + sidx) + 1.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = fmaf(wt1, e[j], acc[j]);
+      } else if (OP == OP_GWT) {
+        // d loss / d wt_v = sum_c g_vol[c] e[c] / n_src: the only thing the scalar chain's backward needs
+        float gwt = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gwt = fmaf(gv.v[j] * inv_nsrc, e[j], gwt);
+#pragma unroll
+        for (int o = LPP / 2; o > 0; o >>= 1) gwt += __shfl_xor_sync(0xffffffffu, gwt, o);
+        if (q == 0 && live) P.s_vol[sidx] = gwt;
       } else {
         float ge[8], g[8];
         if (OP == OP_SCORE_BWD) {
@@ -99,6 +107,14 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             ge[j] = gs * w1[j];
+            if (live) gw1[j] = fmaf(gs, e[j], gw1[j]);
+          }
+        } else if (OP == OP_MERGED_BWD) {
+          // both paths into e at once: through the aggregate (weight held fixed) and through the score
+          const float wt1 = __ldg(P.wt_vol + sidx) + 1.f, gs = __ldg(P.s_vol + sidx);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            ge[j] = fmaf(gv.v[j] * inv_nsrc, wt1, gs * w1[j]);
             if (live) gw1[j] = fmaf(gs, e[j], gw1[j]);
           }
         } else {
@@ -130,7 +146,7 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
       store8(vol + d * vol_stride, r);
     }
   }
-  if (OP == OP_SCORE_BWD || OP == OP_WEIGHTED_BWD) {
+  if (OP == OP_SCORE_BWD || OP == OP_WEIGHTED_BWD || OP == OP_MERGED_BWD) {
     if (live) {
       float* gr = P.g_ref + (long long)b * img_stride + pix * C + c0;   // this thread is the only writer of its 8 channels
       F8 r = load8(gr);
@@ -139,7 +155,7 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
       store8(gr, r);
     }
   }
-  if (OP == OP_SCORE_BWD && P.g_w1) {
+  if ((OP == OP_SCORE_BWD || OP == OP_MERGED_BWD) && P.g_w1) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) atomicAdd(&s_gw[c0 + j], gw1[j]);
     __syncthreads();
@@ -240,4 +256,30 @@ extern "C" int damvs_warp_weighted_bwd(const float* ref_nhwc, const float* const
   DAMVS_REQUIRE(g_dtype == DAMVS_F32 || g_dtype == DAMVS_BF16, "warp_weighted_bwd: bad g_dtype");
   P.wt_vol = wt_vol; P.vol = const_cast<void*>(g_vol); P.g_ref = g_ref; P.s_vol = g_wt_vol;
   return dispatch_train<OP_WEIGHTED_BWD>(P, C, g_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int damvs_warp_gwt(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans, const float* depth_hyp,
+                              const void* g_vol, int g_dtype, float* g_wt_vol, int B, int C, int D, int H, int W, int per_pixel_hyp,
+                              void* stream) {
+  WarpTrainParams P;
+  int rc = fill_common(P, ref_nhwc, src_nhwc, nullptr, n_src, rot_trans, depth_hyp, B, D, H, W, per_pixel_hyp);
+  if (rc) return rc;
+  DAMVS_REQUIRE(g_vol && g_wt_vol && aligned16(g_vol), "warp_gwt: null or misaligned pointer");
+  DAMVS_REQUIRE(g_dtype == DAMVS_F32 || g_dtype == DAMVS_BF16, "warp_gwt: bad g_dtype");
+  P.vol = const_cast<void*>(g_vol); P.s_vol = g_wt_vol;
+  return dispatch_train<OP_GWT>(P, C, g_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int damvs_warp_merged_bwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
+                                     const float* depth_hyp, const float* w1, const float* wt_vol, const float* g_s_vol, const void* g_vol,
+                                     int g_dtype, float* g_ref, float* const* g_src, float* g_w1, int B, int C, int D, int H, int W,
+                                     int per_pixel_hyp, void* stream) {
+  WarpTrainParams P;
+  int rc = fill_common(P, ref_nhwc, src_nhwc, g_src, n_src, rot_trans, depth_hyp, B, D, H, W, per_pixel_hyp);
+  if (rc) return rc;
+  DAMVS_REQUIRE(w1 && wt_vol && g_s_vol && g_vol && g_ref && g_src && aligned16(g_ref) && aligned16(g_vol),
+                "warp_merged_bwd: null or misaligned pointer");
+  DAMVS_REQUIRE(g_dtype == DAMVS_F32 || g_dtype == DAMVS_BF16, "warp_merged_bwd: bad g_dtype");
+  P.w1 = w1; P.wt_vol = wt_vol; P.s_vol = const_cast<float*>(g_s_vol); P.vol = const_cast<void*>(g_vol); P.g_ref = g_ref; P.g_w1 = g_w1;
+  return dispatch_train<OP_MERGED_BWD>(P, C, g_dtype, (cudaStream_t)stream);
 }

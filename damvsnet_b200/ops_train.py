@@ -219,3 +219,25 @@ def warp_weighted_bwd(ref, srcs, rot_trans, depth_values, wt_vol, g_vol, g_ref, 
                                                        _p(wt_vol.contiguous()), _p(g_vol.contiguous()), _dt(g_vol.dtype), _p(g_ref),
                                                        _ptrs(g_srcs), _p(g_wt), b, c, d, h, w, per_pixel, _stream()))
     return g_wt
+
+
+def warp_gwt(ref, srcs, rot_trans, depth_values, g_vol) -> torch.Tensor:
+    """d loss / d wt_v = sum_c g_vol[c] (ref - warp_v)[c]^2 / n_src -> fp32 [n_src,B,D,H,W]; no feature gradients."""
+    b, h, w, c, d, dv, per_pixel = _warp_common(ref, srcs, rot_trans, depth_values)
+    g_wt = torch.empty((len(srcs), b, d, h, w), dtype=torch.float32, device=ref.device)
+    with torch.cuda.device_of(ref):
+        _lib.check(_lib.load().damvs_warp_gwt(_p(ref.contiguous()), _ptrs(srcs), len(srcs), _p(rot_trans.contiguous()), _p(dv),
+                                              _p(g_vol.contiguous()), _dt(g_vol.dtype), _p(g_wt), b, c, d, h, w, per_pixel, _stream()))
+    return g_wt
+
+
+def warp_merged_bwd(ref, srcs, rot_trans, depth_values, w1, wt_vol, g_s_vol, g_vol, g_ref, g_srcs: List[torch.Tensor]) -> torch.Tensor:
+    """One scatter for both paths into the features (through the aggregate and through the score); returns g_w1 [C]."""
+    b, h, w, c, d, dv, per_pixel = _warp_common(ref, srcs, rot_trans, depth_values)
+    g_w1 = torch.zeros(c, dtype=torch.float32, device=ref.device)
+    with torch.cuda.device_of(ref):
+        _lib.check(_lib.load().damvs_warp_merged_bwd(_p(ref.contiguous()), _ptrs(srcs), len(srcs), _p(rot_trans.contiguous()), _p(dv),
+                                                     _p(_f32c(w1, c, "w1")), _p(wt_vol.contiguous()), _p(g_s_vol.contiguous().float()),
+                                                     _p(g_vol.contiguous()), _dt(g_vol.dtype), _p(g_ref), _ptrs(g_srcs), _p(g_w1),
+                                                     b, c, d, h, w, per_pixel, _stream()))
+    return g_w1

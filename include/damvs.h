@@ -268,6 +268,16 @@ int damvs_cross_view_select(const uint16_t* maskbits, const float* losses, int n
 int damvs_cross_view_bwd(const float* depth_est, const float* depth_gt, const float* const* view_imgs, const float* cams,
                          const float* coeff, int B, int n_src, int H, int W, float* g_depth, void* stream);
 
+/* The backward of the pair in two passes instead of two scatters: damvs_warp_gwt writes only d loss / d wt_v (no
+ * feature gradients); after the caller has pushed it through the scalar chain to d loss / d s_v, damvs_warp_merged_bwd
+ * scatters both contributions to the features at once (g_ref, g_src, g_w1 ACCUMULATED).                          */
+int damvs_warp_gwt(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans, const float* depth_hyp,
+                   const void* g_vol, int g_dtype, float* g_wt_vol, int B, int C, int D, int H, int W, int per_pixel_hyp, void* stream);
+int damvs_warp_merged_bwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
+                          const float* depth_hyp, const float* w1, const float* wt_vol, const float* g_s_vol, const void* g_vol,
+                          int g_dtype, float* g_ref, float* const* g_src, float* g_w1, int B, int C, int D, int H, int W,
+                          int per_pixel_hyp, void* stream);
+
 /* Number of kernel launches this library has issued in this process (for bench.py's gpu_launches). */
 uint64_t damvs_launch_count(void);
 
