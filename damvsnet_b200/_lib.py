@@ -59,10 +59,6 @@ _SIGNATURES = {
                              + [c_void_p]),
     "damvs_warp_weighted_fwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p]
                                 + [c_int] * 7 + [c_void_p]),
-    "damvs_warp_score_bwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                     POINTER(c_void_p), c_void_p] + [c_int] * 6 + [c_void_p]),
-    "damvs_warp_weighted_bwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
-                                        c_void_p, POINTER(c_void_p), c_void_p] + [c_int] * 6 + [c_void_p]),
     "damvs_uncertainty_samples_fwd": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "damvs_geo_consistency_fuse": (c_int, [c_void_p] * 4 + [POINTER(c_void_p), POINTER(c_double), c_int, c_int, c_int, c_float, c_float, c_float,
                                            c_double, c_double] + [c_void_p] * 5),
@@ -72,6 +68,9 @@ _SIGNATURES = {
     "damvs_warp_gwt": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p] + [c_int] * 6 + [c_void_p]),
     "damvs_warp_merged_bwd": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                       c_void_p, POINTER(c_void_p), c_void_p] + [c_int] * 6 + [c_void_p]),
+    "damvs_wnet_chain_fwd": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "damvs_wnet_chain_bwd": (c_int, [c_void_p, c_void_p, c_int, c_longlong, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "damvs_launch_count": (c_uint64, []),
 }
 

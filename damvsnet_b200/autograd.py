@@ -12,8 +12,8 @@ kernel of libdamvs_b200.so.
 * ``ProbConvFn``   the final 8 -> 1 convolution writing fp32 logits.
 * ``HeadFn``       softmax + depth + confidence + variance; closed-form backward kernel.
 * ``WarpAggFn``    fused warp + aggregation with a per-voxel weight net (eval-mode BN) or variance aggregation.
-* ``WarpScoreFn`` / ``WarpWeightedFn``  the two halves of the adaptive aggregation when the weight net's
-  BatchNorms use batch statistics (see csrc/warp_agg_train.cu).
+* ``WarpAdaptiveTrainFn``  the adaptive aggregation when the weight net's BatchNorms use batch statistics: score ->
+  native scalar chain -> weighted, one scatter pass in the backward (csrc/warp_agg_train.cu, csrc/wnet_chain.cu).
 """
 from __future__ import annotations
 
@@ -183,74 +183,35 @@ class WarpAggFn(torch.autograd.Function):
         return (g_wnet, None, None, None, None, g_ref, *g_srcs)
 
 
-class WarpScoreFn(torch.autograd.Function):
-    """s_v = sum_c w1[c] (ref - warp_v)[c]^2 -> fp32 [n_src,B,D,H,W]."""
-
-    @staticmethod
-    def forward(ctx, w1, rot_trans, depth_values, ref, *srcs):
-        ctx.save_for_backward(w1, rot_trans, depth_values, ref, *srcs)
-        return ops_train.warp_score_fwd(ref, list(srcs), rot_trans, depth_values, w1)
-
-    @staticmethod
-    def backward(ctx, g_s):
-        w1, rot_trans, dv, ref, *srcs = ctx.saved_tensors
-        g_ref = torch.zeros_like(ref)
-        g_srcs = [torch.zeros_like(s) for s in srcs]
-        g_w1 = ops_train.warp_score_bwd(ref, srcs, rot_trans, dv, w1, g_s, g_ref, g_srcs)
-        return (g_w1, None, None, g_ref, *g_srcs)
-
-
-class WarpWeightedFn(torch.autograd.Function):
-    """vol = sum_v (wt_v + 1) (ref - warp_v)^2 / n_src with wt given as fp32 [n_src,B,D,H,W]."""
-
-    @staticmethod
-    def forward(ctx, wt_vol, rot_trans, depth_values, out_dtype, ref, *srcs):
-        ctx.save_for_backward(wt_vol, rot_trans, depth_values, ref, *srcs)
-        return ops_train.warp_weighted_fwd(ref, list(srcs), rot_trans, depth_values, wt_vol, out_dtype)
-
-    @staticmethod
-    def backward(ctx, g_vol):
-        wt_vol, rot_trans, dv, ref, *srcs = ctx.saved_tensors
-        g_ref = torch.zeros_like(ref)
-        g_srcs = [torch.zeros_like(s) for s in srcs]
-        g_wt = ops_train.warp_weighted_bwd(ref, srcs, rot_trans, dv, wt_vol, g_vol, g_ref, g_srcs)
-        return (g_wt, None, None, None, g_ref, *g_srcs)
-
-
 class WarpAdaptiveTrainFn(torch.autograd.Function):
     """The adaptive aggregation with the weight net in training mode as ONE node: score -> scalar chain -> weighted in
     the forward; in the backward d loss / d wt (no scatter), the chain's own backward on the scalar volumes, then a
     single scatter pass that carries both paths into the features (through the aggregate and through the score).
-    `wn` is the AggWeightNetVolume module (its BatchNorm buffers are updated once, in the forward)."""
+    Every step is a kernel of the library (csrc/warp_agg_train.cu, csrc/wnet_chain.cu).  `wn` is the
+    AggWeightNetVolume module (its BatchNorm buffers are updated once, in the forward)."""
 
     @staticmethod
     def forward(ctx, w1, g1, b1, w2, g2, b2, rot_trans, depth_values, out_dtype, wn, ref, *srcs):
         srcs = list(srcs)
+        a, b = wn.w_net[0], wn.w_net[1]
         s_vol = ops_train.warp_score_fwd(ref, srcs, rot_trans, depth_values, w1.detach().reshape(-1).float())
-        with torch.enable_grad():
-            s_leaf = s_vol.detach().requires_grad_(True)
-            wt_vol = wn.score_to_weight(s_leaf)       # uses g1, b1, w2, g2, b2 (the module's own parameters)
-        vol = ops_train.warp_weighted_fwd(ref, srcs, rot_trans, depth_values, wt_vol.detach(), out_dtype)
-        ctx.chain = (s_leaf, wt_vol, (g1, b1, w2, g2, b2))
-        ctx.save_for_backward(w1, rot_trans, depth_values, ref, *srcs)
+        wt_vol, state = ops_train.wnet_chain_fwd(s_vol, a.bn, w2, b.bn)
+        vol = ops_train.warp_weighted_fwd(ref, srcs, rot_trans, depth_values, wt_vol, out_dtype)
+        ctx.save_for_backward(w1, w2, s_vol, wt_vol, state, rot_trans, depth_values, ref, *srcs)
         return vol
 
     @staticmethod
     def backward(ctx, g_vol):
-        w1, rot_trans, dv, ref, *srcs = ctx.saved_tensors
-        s_leaf, wt_vol, chain_params = ctx.chain
+        w1, w2, s_vol, wt_vol, state, rot_trans, dv, ref, *srcs = ctx.saved_tensors
         g_wt = ops_train.warp_gwt(ref, srcs, rot_trans, dv, g_vol)
-        wanted = [s_leaf] + [p for p in chain_params if p.requires_grad]
-        grads = torch.autograd.grad(wt_vol, wanted, g_wt, allow_unused=True)
-        g_s = grads[0] if grads[0] is not None else torch.zeros_like(s_leaf)
-        it = iter(grads[1:])
-        g_chain = [next(it) if p.requires_grad else None for p in chain_params]
+        g_s, gp = ops_train.wnet_chain_bwd(s_vol, g_wt, state, w2)
         g_ref = torch.zeros_like(ref)
         g_srcs = [torch.zeros_like(s) for s in srcs]
-        g_w1 = ops_train.warp_merged_bwd(ref, srcs, rot_trans, dv, w1.detach().reshape(-1).float(), wt_vol.detach(), g_s, g_vol,
-                                         g_ref, g_srcs)
-        ctx.chain = None
-        return (g_w1.view_as(w1), *g_chain, None, None, None, None, g_ref, *g_srcs)
+        g_w1 = ops_train.warp_merged_bwd(ref, srcs, rot_trans, dv, w1.detach().reshape(-1).float(), wt_vol, g_s, g_vol, g_ref, g_srcs)
+        need = ctx.needs_input_grad
+        return (g_w1.view_as(w1) if need[0] else None, gp[0:1] if need[1] else None, gp[1:2] if need[2] else None,
+                gp[2:3].view_as(w2) if need[3] else None, gp[3:4] if need[4] else None, gp[4:5] if need[5] else None,
+                None, None, None, None, g_ref, *g_srcs)
 
 
 def wants_grad(*tensors: Optional[torch.Tensor]) -> bool:

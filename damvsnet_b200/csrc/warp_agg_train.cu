@@ -6,15 +6,16 @@
 // statistics -- and its running buffers -- are per view), which makes the weight non-local.  The adaptive
 // aggregation then factors into
 //     s_v   = sum_c w1[c] (ref - warp_v)[c]^2                    "score"    (this file, native)
-//     wt_v  = relu(bn2(w2 * relu(bn1(s_v))))                     scalar volumes, 1/C of the data: host side
-//     vol   = sum_v (wt_v + 1) (ref - warp_v)^2 / n_src          "weighted" (this file, native)
-// and the backward into the mirrored pair.  Every kernel re-projects and re-samples instead of storing the
+//     wt_v  = relu(bn2(w2 * relu(bn1(s_v))))                     scalar volumes, 1/C of the data (wnet_chain.cu)
+//     vol   = sum_v (wt_v + 1) (ref - warp_v)^2 / n_src          "weighted" (this file)
+// and the backward into: d loss / d wt_v without any scatter ("gwt"), the chain's backward, and ONE scatter pass that
+// carries both paths into the features ("merged").  Every kernel re-projects and re-samples instead of storing the
 // N x D warped volumes.  Thread = (pixel, 8 channels), the C/8 lanes of a pixel adjacent in the warp.
 #include "warp_common.cuh"
 
 namespace damvs {
 
-enum { OP_SCORE_FWD = 0, OP_WEIGHTED_FWD = 1, OP_SCORE_BWD = 2, OP_WEIGHTED_BWD = 3, OP_GWT = 4, OP_MERGED_BWD = 5 };
+enum { OP_SCORE_FWD = 0, OP_WEIGHTED_FWD = 1, OP_GWT = 2, OP_MERGED_BWD = 3 };
 
 struct WarpTrainParams {
   const float* ref;
@@ -24,8 +25,8 @@ struct WarpTrainParams {
   const float* hyp;
   const float* w1;       // [C]                       (score ops)
   const float* wt_vol;   // [n_src][B][D][H][W]       (weighted ops)
-  float* s_vol;          // score fwd: out; score bwd: g_s in; weighted bwd / gwt: g_wt out; merged bwd: g_s in
-  void* vol;             // weighted fwd: out (G8); weighted bwd: g_vol in (G8)
+  float* s_vol;          // score fwd: out; gwt: g_wt out; merged bwd: g_s in
+  void* vol;             // weighted fwd: out (G8); gwt / merged bwd: g_vol in (G8)
   float* g_ref;          // accumulated
   float* g_w1;           // accumulated [C]
   int B, n_src, D, H, W, per_pixel;
@@ -40,7 +41,7 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
   const int b = blockIdx.z, H = P.H, W = P.W, D = P.D, n_src = P.n_src;
   for (int i = threadIdx.x; i < n_src * 12; i += blockDim.x) s_rt[i] = P.rot_trans[((long long)(i / 12) * P.B + b) * 12 + i % 12];
   for (int i = threadIdx.x; i < C; i += blockDim.x) {
-    s_w1[i] = (OP == OP_SCORE_FWD || OP == OP_SCORE_BWD || OP == OP_MERGED_BWD) ? P.w1[i] : 0.f;
+    s_w1[i] = (OP == OP_SCORE_FWD || OP == OP_MERGED_BWD) ? P.w1[i] : 0.f;
     s_gw[i] = 0.f;
   }
   __syncthreads();
@@ -72,7 +73,7 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j] = 0.f; gv.v[j] = 0.f; }
-    if (OP == OP_WEIGHTED_BWD || OP == OP_GWT || OP == OP_MERGED_BWD) gv = load8(vol + d * vol_stride);
+    if (OP == OP_GWT || OP == OP_MERGED_BWD) gv = load8(vol + d * vol_stride);
     for (int v = 0; v < n_src; ++v) {
       float ix, iy, w[4], wv[8], df[8], e[8];
       project_b(s_rt + v * 12, fx, fy, dep, inv_half_w, inv_half_h, fw, fh, ix, iy);
@@ -101,34 +102,13 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
         for (int o = LPP / 2; o > 0; o >>= 1) gwt += __shfl_xor_sync(0xffffffffu, gwt, o);
         if (q == 0 && live) P.s_vol[sidx] = gwt;
       } else {
+        // merged backward: both paths into e at once, through the aggregate (weight held fixed) and through the score
         float ge[8], g[8];
-        if (OP == OP_SCORE_BWD) {
-          const float gs = __ldg(P.s_vol + sidx);
+        const float wt1 = __ldg(P.wt_vol + sidx) + 1.f, gs = __ldg(P.s_vol + sidx);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            ge[j] = gs * w1[j];
-            if (live) gw1[j] = fmaf(gs, e[j], gw1[j]);
-          }
-        } else if (OP == OP_MERGED_BWD) {
-          // both paths into e at once: through the aggregate (weight held fixed) and through the score
-          const float wt1 = __ldg(P.wt_vol + sidx) + 1.f, gs = __ldg(P.s_vol + sidx);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            ge[j] = fmaf(gv.v[j] * inv_nsrc, wt1, gs * w1[j]);
-            if (live) gw1[j] = fmaf(gs, e[j], gw1[j]);
-          }
-        } else {
-          const float wt1 = __ldg(P.wt_vol + sidx) + 1.f;
-          float gwt = 0.f;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float gvn = gv.v[j] * inv_nsrc;
-            gwt = fmaf(gvn, e[j], gwt);
-            ge[j] = gvn * wt1;
-          }
-#pragma unroll
-          for (int o = LPP / 2; o > 0; o >>= 1) gwt += __shfl_xor_sync(0xffffffffu, gwt, o);
-          if (q == 0 && live) P.s_vol[sidx] = gwt;
+        for (int j = 0; j < 8; ++j) {
+          ge[j] = fmaf(gv.v[j] * inv_nsrc, wt1, gs * w1[j]);
+          if (live) gw1[j] = fmaf(gs, e[j], gw1[j]);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -146,7 +126,7 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
       store8(vol + d * vol_stride, r);
     }
   }
-  if (OP == OP_SCORE_BWD || OP == OP_WEIGHTED_BWD || OP == OP_MERGED_BWD) {
+  if (OP == OP_MERGED_BWD) {
     if (live) {
       float* gr = P.g_ref + (long long)b * img_stride + pix * C + c0;   // this thread is the only writer of its 8 channels
       F8 r = load8(gr);
@@ -155,7 +135,7 @@ __global__ void __launch_bounds__(128) warp_train_kernel(const WarpTrainParams P
       store8(gr, r);
     }
   }
-  if ((OP == OP_SCORE_BWD || OP == OP_MERGED_BWD) && P.g_w1) {
+  if (OP == OP_MERGED_BWD && P.g_w1) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) atomicAdd(&s_gw[c0 + j], gw1[j]);
     __syncthreads();
@@ -230,32 +210,6 @@ extern "C" int damvs_warp_weighted_fwd(const float* ref_nhwc, const float* const
   DAMVS_REQUIRE(out_dtype == DAMVS_F32 || out_dtype == DAMVS_BF16, "warp_weighted_fwd: bad out_dtype");
   P.wt_vol = wt_vol; P.vol = out_vol;
   return dispatch_train<OP_WEIGHTED_FWD>(P, C, out_dtype, (cudaStream_t)stream);
-}
-
-extern "C" int damvs_warp_score_bwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
-                                    const float* depth_hyp, const float* w1, const float* g_s_vol, float* g_ref,
-                                    float* const* g_src, float* g_w1, int B, int C, int D, int H, int W, int per_pixel_hyp,
-                                    void* stream) {
-  WarpTrainParams P;
-  int rc = fill_common(P, ref_nhwc, src_nhwc, g_src, n_src, rot_trans, depth_hyp, B, D, H, W, per_pixel_hyp);
-  if (rc) return rc;
-  DAMVS_REQUIRE(w1 && g_s_vol && g_ref && g_src && aligned16(g_ref), "warp_score_bwd: null or misaligned pointer");
-  P.w1 = w1; P.s_vol = const_cast<float*>(g_s_vol); P.g_ref = g_ref; P.g_w1 = g_w1;
-  return dispatch_train<OP_SCORE_BWD>(P, C, DAMVS_F32, (cudaStream_t)stream);
-}
-
-extern "C" int damvs_warp_weighted_bwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
-                                       const float* depth_hyp, const float* wt_vol, const void* g_vol, int g_dtype,
-                                       float* g_ref, float* const* g_src, float* g_wt_vol, int B, int C, int D, int H, int W,
-                                       int per_pixel_hyp, void* stream) {
-  WarpTrainParams P;
-  int rc = fill_common(P, ref_nhwc, src_nhwc, g_src, n_src, rot_trans, depth_hyp, B, D, H, W, per_pixel_hyp);
-  if (rc) return rc;
-  DAMVS_REQUIRE(wt_vol && g_vol && g_ref && g_src && g_wt_vol && aligned16(g_ref) && aligned16(g_vol),
-                "warp_weighted_bwd: null or misaligned pointer");
-  DAMVS_REQUIRE(g_dtype == DAMVS_F32 || g_dtype == DAMVS_BF16, "warp_weighted_bwd: bad g_dtype");
-  P.wt_vol = wt_vol; P.vol = const_cast<void*>(g_vol); P.g_ref = g_ref; P.s_vol = g_wt_vol;
-  return dispatch_train<OP_WEIGHTED_BWD>(P, C, g_dtype, (cudaStream_t)stream);
 }
 
 extern "C" int damvs_warp_gwt(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans, const float* depth_hyp,

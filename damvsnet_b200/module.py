@@ -259,7 +259,7 @@ class AggWeightNetVolume(nn.Module):
         """[C+5] fp32: w1[C], scale1, shift1, w2, scale2, shift2 (include/damvs.h, damvs_warp_agg_fwd)."""
         a, b = self.w_net[0], self.w_net[1]
         if self.training:
-            raise RuntimeError("folded() is the eval-mode form; in training DepthNet uses score -> chain -> weighted")
+            raise RuntimeError("folded() is the eval-mode form; in training DepthNet runs autograd.WarpAdaptiveTrainFn")
         tensors = (a.conv.weight, a.bn.weight, a.bn.bias, a.bn.running_mean, a.bn.running_var,
                    b.conv.weight, b.bn.weight, b.bn.bias, b.bn.running_mean, b.bn.running_var)
         ver = _versions(*tensors)
@@ -285,36 +285,6 @@ class AggWeightNetVolume(nn.Module):
         s1, b1 = affine(a.bn)
         s2, b2 = affine(b.bn)
         return torch.cat([a.conv.weight.reshape(-1), s1, b1, b.conv.weight.reshape(-1), s2, b2]).float().contiguous()
-
-    @staticmethod
-    def _bn_scalar(x: torch.Tensor, bn: nn.BatchNorm3d) -> torch.Tensor:
-        """nn.BatchNorm3d(1) in training mode on a single-channel volume, written out (one var_mean reduction +
-        elementwise ops, differentiable): cuDNN's batch-norm kernels run a one-channel tensor on ONE thread
-        block (measured 10 ms per call at the training shape).  Running buffers are updated as
-        nn.BatchNorm3d.forward does (momentum, unbiased variance, num_batches_tracked)."""
-        var, mean = torch.var_mean(x, unbiased=False)
-        with torch.no_grad():
-            if bn.track_running_stats and bn.running_mean is not None:
-                n = x.numel()
-                bn.num_batches_tracked += 1
-                f = 1.0 / float(bn.num_batches_tracked) if bn.momentum is None else bn.momentum
-                bn.running_mean.mul_(1 - f).add_(mean.detach().reshape(1), alpha=f)
-                bn.running_var.mul_(1 - f).add_((var.detach() * (n / max(n - 1, 1))).reshape(1), alpha=f)
-        return (x - mean) * (torch.rsqrt(var + bn.eps) * bn.weight.reshape(())) + bn.bias.reshape(())
-
-    def score_to_weight(self, s_vol: torch.Tensor) -> torch.Tensor:
-        """Training-mode tail of the net on per-view score volumes [n_src,B,D,H,W] -> weights, same shape.
-        s_v is the output of w_net[0].conv; what follows is BatchNorm3d(1) -> ReLU -> 1x1x1 conv (a scalar) ->
-        BatchNorm3d(1) -> ReLU, evaluated once per source view exactly as models/cas_mvsnet.py:71 calls the net,
-        so the batch statistics and the running-buffer updates are per view.  These are scalar volumes (1/C of
-        the cost volume) and the chain is host-side tensor algebra on them."""
-        a, b = self.w_net[0], self.w_net[1]
-        out = []
-        for v in range(s_vol.shape[0]):
-            x = torch.relu(self._bn_scalar(s_vol[v], a.bn))
-            x = torch.relu(self._bn_scalar(x * b.conv.weight.reshape(()), b.bn))
-            out.append(x)
-        return torch.stack(out, 0)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """Stand-alone reference signature [B,C,D,H,W] -> [B,1,D,H,W].  Not used by DepthNet (fused there);

@@ -199,28 +199,6 @@ def warp_weighted_fwd(ref, srcs, rot_trans, depth_values, wt_vol: torch.Tensor, 
     return out
 
 
-def warp_score_bwd(ref, srcs, rot_trans, depth_values, w1, g_s_vol, g_ref, g_srcs: List[torch.Tensor]) -> torch.Tensor:
-    """Accumulates into g_ref / g_srcs; returns g_w1 [C]."""
-    b, h, w, c, d, dv, per_pixel = _warp_common(ref, srcs, rot_trans, depth_values)
-    g_w1 = torch.zeros(c, dtype=torch.float32, device=ref.device)
-    with torch.cuda.device_of(ref):
-        _lib.check(_lib.load().damvs_warp_score_bwd(_p(ref.contiguous()), _ptrs(srcs), len(srcs), _p(rot_trans.contiguous()), _p(dv),
-                                                    _p(_f32c(w1, c, "w1")), _p(g_s_vol.contiguous().float()), _p(g_ref), _ptrs(g_srcs),
-                                                    _p(g_w1), b, c, d, h, w, per_pixel, _stream()))
-    return g_w1
-
-
-def warp_weighted_bwd(ref, srcs, rot_trans, depth_values, wt_vol, g_vol, g_ref, g_srcs: List[torch.Tensor]) -> torch.Tensor:
-    """Accumulates into g_ref / g_srcs; returns g_wt_vol [n_src,B,D,H,W]."""
-    b, h, w, c, d, dv, per_pixel = _warp_common(ref, srcs, rot_trans, depth_values)
-    g_wt = torch.empty((len(srcs), b, d, h, w), dtype=torch.float32, device=ref.device)
-    with torch.cuda.device_of(ref):
-        _lib.check(_lib.load().damvs_warp_weighted_bwd(_p(ref.contiguous()), _ptrs(srcs), len(srcs), _p(rot_trans.contiguous()), _p(dv),
-                                                       _p(wt_vol.contiguous()), _p(g_vol.contiguous()), _dt(g_vol.dtype), _p(g_ref),
-                                                       _ptrs(g_srcs), _p(g_wt), b, c, d, h, w, per_pixel, _stream()))
-    return g_wt
-
-
 def warp_gwt(ref, srcs, rot_trans, depth_values, g_vol) -> torch.Tensor:
     """d loss / d wt_v = sum_c g_vol[c] (ref - warp_v)[c]^2 / n_src -> fp32 [n_src,B,D,H,W]; no feature gradients."""
     b, h, w, c, d, dv, per_pixel = _warp_common(ref, srcs, rot_trans, depth_values)
@@ -241,3 +219,44 @@ def warp_merged_bwd(ref, srcs, rot_trans, depth_values, w1, wt_vol, g_s_vol, g_v
                                                      _p(g_vol.contiguous()), _dt(g_vol.dtype), _p(g_ref), _ptrs(g_srcs), _p(g_w1),
                                                      b, c, d, h, w, per_pixel, _stream()))
     return g_w1
+
+
+def wnet_chain_fwd(s_vol: torch.Tensor, bn1, w2: torch.Tensor, bn2):
+    """Scalar tail of the weight net with batch statistics per view: s_vol [n_src,B,D,H,W] -> (wt_vol, state [n_src,8]).
+    bn1 / bn2 are the nn.BatchNorm3d(1) modules: their affine parameters are read, their running buffers updated view by
+    view (momentum must be a number), num_batches_tracked advanced by n_src."""
+    n = s_vol.shape[0]
+    m = s_vol.numel() // n
+    dev = s_vol.device
+    if bn1.momentum is None or bn2.momentum is None or bn1.momentum != bn2.momentum or bn1.eps != bn2.eps:
+        raise NotImplementedError("native weight-net chain needs one numeric BatchNorm momentum and eps")
+    sums = torch.zeros(4 * n, dtype=torch.float64, device=dev)
+    state = torch.empty((n, 8), dtype=torch.float32, device=dev)
+    wt = torch.empty_like(s_vol)
+    track = bn1.track_running_stats and bn1.running_mean is not None
+    with torch.no_grad():
+        if track:
+            bn1.num_batches_tracked += n
+            bn2.num_batches_tracked += n
+    with torch.cuda.device_of(s_vol):
+        _lib.check(_lib.load().damvs_wnet_chain_fwd(
+            _p(s_vol.contiguous()), n, m, _p(bn1.weight.detach()), _p(bn1.bias.detach()), _p(bn1.running_mean if track else None),
+            _p(bn1.running_var if track else None), _p(w2.detach().reshape(-1).float()), _p(bn2.weight.detach()), _p(bn2.bias.detach()),
+            _p(bn2.running_mean if track else None), _p(bn2.running_var if track else None), float(bn1.momentum), float(bn1.eps),
+            _p(sums), _p(state), _p(wt), _stream()))
+    return wt, state
+
+
+def wnet_chain_bwd(s_vol: torch.Tensor, g_wt: torch.Tensor, state: torch.Tensor, w2: torch.Tensor):
+    """Backward of wnet_chain_fwd: (g_s [n_src,B,D,H,W], g_params [5] = d gamma1, d beta1, d w2, d gamma2, d beta2)."""
+    n = s_vol.shape[0]
+    m = s_vol.numel() // n
+    dev = s_vol.device
+    sums = torch.zeros(4 * n + 2, dtype=torch.float64, device=dev)
+    coef = torch.empty((n, 6), dtype=torch.float32, device=dev)
+    g_s = torch.empty_like(s_vol)
+    g_params = torch.empty(5, dtype=torch.float32, device=dev)
+    with torch.cuda.device_of(s_vol):
+        _lib.check(_lib.load().damvs_wnet_chain_bwd(_p(s_vol.contiguous()), _p(g_wt.contiguous()), n, m, _p(state), _p(w2.detach().reshape(-1).float()),
+                                                    _p(sums), _p(coef), _p(g_s), _p(g_params), _stream()))
+    return g_s, g_params

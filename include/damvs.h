@@ -211,21 +211,14 @@ int damvs_warp_agg_bwd(const float* ref_nhwc, const float* const* src_nhwc, int 
 /* ---- warp + aggregation with the view-weight net in training mode (batch statistics) --------------------
  * AggWeightNetVolume's BatchNorms (models/module.py:548-551) then normalise over a whole per-view score volume,
  * so the adaptive aggregation splits into  s_v = sum_c w1[c] (ref - warp_v)[c]^2  ("score"),  the scalar
- * chain s_v -> wt_v on [n_src][B][D][H][W] fp32 volumes (caller), and
- * vol = sum_v (wt_v + 1)(ref - warp_v)^2 / n_src ("weighted").  g_ref / g_src / g_w1 are ACCUMULATED.      */
+ * chain s_v -> wt_v on [n_src][B][D][H][W] fp32 volumes (damvs_wnet_chain_fwd), and
+ * vol = sum_v (wt_v + 1)(ref - warp_v)^2 / n_src ("weighted").                                                */
 int damvs_warp_score_fwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
                          const float* depth_hyp, const float* w1, float* s_vol, int B, int C, int D, int H, int W,
                          int per_pixel_hyp, void* stream);
 int damvs_warp_weighted_fwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
                             const float* depth_hyp, const float* wt_vol, void* out_vol, int B, int C, int D, int H, int W,
                             int per_pixel_hyp, int out_dtype, void* stream);
-int damvs_warp_score_bwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
-                         const float* depth_hyp, const float* w1, const float* g_s_vol, float* g_ref, float* const* g_src,
-                         float* g_w1, int B, int C, int D, int H, int W, int per_pixel_hyp, void* stream);
-int damvs_warp_weighted_bwd(const float* ref_nhwc, const float* const* src_nhwc, int n_src, const float* rot_trans,
-                            const float* depth_hyp, const float* wt_vol, const void* g_vol, int g_dtype, float* g_ref,
-                            float* const* g_src, float* g_wt_vol, int B, int C, int D, int H, int W, int per_pixel_hyp,
-                            void* stream);
 
 /* ---- depth-hypothesis sampling for cascade stages 2/3 (upstream neighbour of the path) ----------------
  * Fuses models/cas_mvsnet.py:250-253 (two bilinear up-samples to full resolution), uncertainty_aware_samples
@@ -267,6 +260,18 @@ int damvs_cross_view_select(const uint16_t* maskbits, const float* losses, int n
                             unsigned long long* counts, void* stream);
 int damvs_cross_view_bwd(const float* depth_est, const float* depth_gt, const float* const* view_imgs, const float* cams,
                          const float* coeff, int B, int n_src, int H, int W, float* g_depth, void* stream);
+
+/* The scalar chain between them, s_v -> wt_v = relu(bn2(w2 relu(bn1(s_v)))) with batch statistics per view (n_src
+ * successive calls of the net in the reference), on [n_src][M] fp32 volumes (M = B*D*H*W); all pointers device.
+ * fwd: sums_ws fp64 [4*n_src] zeroed by the caller; state fp32 [n_src][8] out (per view: a1, c1, mean1, rstd1, a2, c2,
+ *      mean2, rstd2: the folded affines and what the backward needs); running buffers (NULL to skip) updated view by view.
+ * bwd: sums_ws fp64 [4*n_src + 2] zeroed; coef_ws fp32 [n_src][6] scratch; g_s [n_src][M] out;
+ *      g_params [5] out = d gamma1, d beta1, d w2, d gamma2, d beta2 (summed over views).                            */
+int damvs_wnet_chain_fwd(const float* s_vol, int n_src, long long M, const float* gamma1, const float* beta1, float* running_mean1,
+                         float* running_var1, const float* w2, const float* gamma2, const float* beta2, float* running_mean2,
+                         float* running_var2, float momentum, float eps, double* sums_ws, float* state, float* wt_vol, void* stream);
+int damvs_wnet_chain_bwd(const float* s_vol, const float* g_wt, int n_src, long long M, const float* state, const float* w2, double* sums_ws,
+                         float* coef_ws, float* g_s, float* g_params, void* stream);
 
 /* The backward of the pair in two passes instead of two scatters: damvs_warp_gwt writes only d loss / d wt_v (no
  * feature gradients); after the caller has pushed it through the scalar chain to d loss / d s_v, damvs_warp_merged_bwd
