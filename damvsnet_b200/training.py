@@ -2,9 +2,11 @@
 
 One process per GPU.  Each rank runs forward + backward of the three stages on its own batch through the native
 kernels (``damvsnet_b200.autograd``), then the gradients of the hot-path parameters are summed across ranks:
-``GradientBucket`` flattens them into ONE contiguous fp32 buffer (3.5 MB for base_channels 8), one
-``all_reduce`` (NCCL over NVLink on the GPUs, gloo in the CPU test) replaces ~70 per-tensor collectives, and the
-averaged values are scattered back into ``param.grad``.  BatchNorm statistics stay per GPU, as in the reference
+``GradientBucket`` flattens a parameter set into ONE contiguous fp32 buffer (3.5 MB for the whole path at base_channels
+8) so that one ``all_reduce`` (NCCL over NVLink on the GPUs, gloo in the CPU test) replaces ~70 per-tensor
+collectives; ``OverlappedBuckets`` keeps one bucket per cascade stage and starts its collective from gradient hooks as
+soon as that stage's backward is complete, so it overlaps the backward kernels of the remaining stages; the averaged
+values are scattered back into ``param.grad``.  BatchNorm statistics stay per GPU, as in the reference
 (plain ``DistributedDataParallel``, no SyncBN: train.py:474-479); buffers are broadcast from rank 0 once at
 start, like DDP's initial sync.  Parameters that never receive a gradient (the dead ``conv0`` of the view-weight
 net) are left out of the bucket -- the reference as committed needs
@@ -78,6 +80,42 @@ class GradientBucket:
         return None
 
 
+class OverlappedBuckets:
+    """One GradientBucket per cascade stage, all-reduced as soon as the backward pass has produced the last gradient of
+    that stage (autograd runs the stages in reverse, so the collective of stage 3 overlaps the backward kernels of
+    stages 2 and 1).  Hooks fire on gradient accumulation; `finish()` waits for the collectives and scatters the
+    averages back.  Without a process group everything is a no-op."""
+
+    def __init__(self, stage_params: Sequence[Sequence[torch.nn.Parameter]], group=None):
+        self.group = group
+        self.buckets = [GradientBucket(ps) for ps in stage_params if any(p.requires_grad for p in ps)]
+        self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self._left: List[int] = []
+        self._done: List[object] = []
+        if self.active:
+            for i, b in enumerate(self.buckets):
+                for p in b.params:
+                    p.register_post_accumulate_grad_hook(lambda _p, i=i: self._ready(i))
+        self.reset()
+
+    def reset(self) -> None:
+        self._left = [len(b.params) for b in self.buckets]
+        self._done = [None] * len(self.buckets)
+
+    def _ready(self, i: int) -> None:
+        self._left[i] -= 1
+        if self._left[i] == 0:
+            self._done[i] = self.buckets[i].allreduce(self.group, async_op=True)
+
+    def finish(self) -> None:
+        if self.active:
+            for i, b in enumerate(self.buckets):
+                fin = self._done[i] if self._left[i] <= 0 else b.allreduce(self.group, async_op=True)   # a parameter got no gradient
+                if fin is not None:
+                    fin()
+        self.reset()
+
+
 def broadcast_module_state(modules: Sequence[torch.nn.Module], src: int = 0, group=None) -> None:
     """Parameters and buffers of rank `src` to every rank (DDP's construction-time sync)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
@@ -123,7 +161,12 @@ class HotPathTrainer:
         broadcast_module_state([self.depthnet, self.cost_regularization], group=group)
         self.params = [p for p in list(self.depthnet.parameters()) + list(self.cost_regularization.parameters())
                        if p.requires_grad]
-        self.bucket = GradientBucket(self.params)
+        self.bucket = GradientBucket(self.params)          # the whole hot path as one buffer (size report, tests)
+        n_stage = len(self.cost_regularization)
+        per_stage = [[p for p in list(self.cost_regularization[s].parameters()) +
+                      (list(self.depthnet.weight_net[s].parameters()) if mode == "adaptive" else []) if p.requires_grad]
+                     for s in range(n_stage)]
+        self.overlap = OverlappedBuckets(per_stage, group)
         self.optimizer = torch.optim.Adam(self.params, lr=lr, betas=(0.9, 0.999), weight_decay=weight_decay)
 
     def forward(self, stages: Sequence[StageInput]) -> List[Dict[str, torch.Tensor]]:
@@ -143,7 +186,7 @@ class HotPathTrainer:
             named = {f"stage{i + 1}": o for i, o in enumerate(outs)}
             gts = {f"stage{i + 1}": g for i, g in enumerate(depth_gt)}
             loss = loss + cpc_weight * cross_view_loss(named, imgs, sample_cams, gts, list(dlossw))
-        loss.backward()
-        self.bucket.allreduce(self.group)
+        loss.backward()          # per-stage gradient all-reduces start from hooks inside the backward pass
+        self.overlap.finish()
         self.optimizer.step()
         return loss.detach()

@@ -80,3 +80,38 @@ def test_depth_loss_matches_reference_formula():
     got = training.depth_loss(outs, gts, masks, (0.5, 1.0, 2.0))
     want = sum(w * torch.nn.functional.smooth_l1_loss(o["depth"][m > 0.5], t[m > 0.5]) for o, t, m, w in zip(outs, gts, masks, (0.5, 1.0, 2.0)))
     torch.testing.assert_close(got, want)
+
+
+def _overlap_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    stages = [torch.nn.Linear(4, 4) for _ in range(3)]
+    ob = training.OverlappedBuckets([list(m.parameters()) for m in stages])
+    outs = []
+    for step in range(2):                                  # hooks and counters survive several steps
+        for m in stages:
+            m.zero_grad(set_to_none=False)
+        x = torch.full((2, 4), float(rank + 1 + step))
+        (stages[0](x).sum() + 2 * stages[1](x).sum() + 3 * stages[2](x).sum()).backward()
+        local = [p.grad.clone() for m in stages for p in m.parameters()]
+        ob.finish()
+        outs.append((local, [p.grad.clone() for m in stages for p in m.parameters()]))
+    ret[rank] = outs
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_overlapped_stage_buckets_average_gradients():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_overlap_worker, args=(world, port, ret), nprocs=world, join=True)
+        r0, r1 = ret[0], ret[1]
+    for step in range(2):
+        (l0, g0), (l1, g1) = r0[step], r1[step]
+        for a, b, ga, gb in zip(l0, l1, g0, g1):
+            torch.testing.assert_close(ga, (a + b) / 2)
+            torch.testing.assert_close(gb, (a + b) / 2)
