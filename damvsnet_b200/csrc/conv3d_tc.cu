@@ -608,6 +608,11 @@ static bool build_program(int mode, int G, std::vector<StepSrc>& steps) {
 bool conv3d_tcf_supported(const damvs_conv3d_desc* d);
 size_t conv3d_tcf_packed_bytes(const damvs_conv3d_desc* d);
 int conv3d_tcf_pack(const damvs_conv3d_desc* d, const float* weight, void* packed, cudaStream_t st);
+// prob layer (8 -> 1, plain fp32 output): every tap folded into N (conv3d_tcp.cu)
+bool conv3d_tcp_supported(const damvs_conv3d_desc* d);
+size_t conv3d_tcp_packed_bytes(const damvs_conv3d_desc* d);
+int conv3d_tcp_pack(const damvs_conv3d_desc* d, const float* weight, void* packed, cudaStream_t st);
+int conv3d_tcp_launch(const damvs_conv3d_desc* d, const void* in, const void* packed, void* out, cudaStream_t st);
 int conv3d_tcf_launch(const damvs_conv3d_desc* d, const void* in, const void* packed, const float* scale, const float* shift,
                       const void* skip, void* out, cudaStream_t st);
 
@@ -617,6 +622,7 @@ static int n_split(int Cin, int Cout) { return (Cin >= 64 && Cout >= 64) ? 2 : 1
 static size_t blob_bytes(int nsteps, int CP) { return (size_t)weights_offset(nsteps) + (size_t)nsteps * 2 * 3 * CP * 16; }
 
 size_t conv3d_tc_packed_bytes(const damvs_conv3d_desc* d) {
+  if (conv3d_tcp_supported(d)) return conv3d_tcp_packed_bytes(d) + conv3d_tcf_packed_bytes(d);   // odd depths use the depth-folded kernel
   if (conv3d_tcf_supported(d)) return conv3d_tcf_packed_bytes(d);
   std::vector<StepSrc> steps;
   if (!build_program(mode_of(d), d->Cin / 8, steps)) return 0;
@@ -655,6 +661,10 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, uint8_t* __re
 }
 
 int conv3d_tc_pack(const damvs_conv3d_desc* d, const float* weight, void* packed, cudaStream_t st) {
+  if (conv3d_tcp_supported(d)) {
+    const int rc = conv3d_tcp_pack(d, weight, packed, st);
+    return rc != DAMVS_OK ? rc : conv3d_tcf_pack(d, weight, (uint8_t*)packed + conv3d_tcp_packed_bytes(d), st);
+  }
   if (conv3d_tcf_supported(d)) return conv3d_tcf_pack(d, weight, packed, st);
   std::vector<StepSrc> steps;
   const int mode = mode_of(d), G = d->Cin / 8;
@@ -853,6 +863,10 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
   if (d->in_dtype != DAMVS_BF16 || (!d->plain_out && d->out_dtype != DAMVS_BF16))
     return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: bf16 volumes only");
   if (d->plain_out && (d->transposed || d->stride != 1)) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: plain_out is stride-1 only");
+  if (conv3d_tcp_supported(d)) {
+    if (d->Din % 2 == 0) return conv3d_tcp_launch(d, in, packed, out, st);
+    return conv3d_tcf_launch(d, in, (const uint8_t*)packed + conv3d_tcp_packed_bytes(d), scale, shift, skip, out, st);
+  }
   if (conv3d_tcf_supported(d)) return conv3d_tcf_launch(d, in, packed, scale, shift, skip, out, st);
   const int mode = mode_of(d), G = d->Cin / 8;
   if (G != 1 && G % 2) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: Cin=%d not supported", d->Cin);

@@ -72,12 +72,21 @@ def test_tc_conv_block_matches_torch(cin, cout, stride, transposed, ext):
     assert (err <= tol * ws.abs() + tol * want.abs() + 4e-3).all(), err.max().item()
 
 
-def test_tc_prob_conv_plain_output():
+@pytest.mark.parametrize("shape", [
+    (2, 8, 13, 45),       # several tiles, ragged in both directions
+    (1, 5, 7, 33),        # odd depth: the last plane pair is half padding
+    (1, 1, 6, 30),        # a single plane, exactly one tile
+    (1, 2, 3, 5),         # smaller than a tile
+    (1, 48, 20, 70),      # stage-1 depth: the accumulator ring wraps many times
+    (1, 5, 120, 600),     # more tiles than resident CTAs, odd depth: ring position carried across tiles
+    (2, 8, 126, 330),
+])
+def test_tc_prob_conv_plain_output(shape):
     import damvsnet_b200 as dm
     from damvsnet_b200 import ops
     g = torch.Generator().manual_seed(9)
     w = _bf(torch.randn(1, 8, 3, 3, 3, generator=g) * 0.2)
-    x = _bf(torch.randn(2, 8, 8, 13, 45, generator=g))
+    x = _bf(torch.randn(shape[0], 8, *shape[1:], generator=g))
     want = F.conv3d(x, w, None, padding=1).squeeze(1)
     packed = ops.conv3d_pack_weight(w.to(dev()), 8, 1, False, ops.CONV_TCGEN05)
     vol = dm.G8Volume.from_ncdhw(x.to(dev()), torch.bfloat16)

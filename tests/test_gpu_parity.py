@@ -56,6 +56,13 @@ def test_head_matches_oracle(dm, D, per_pixel):
     if not per_pixel:
         want = O.regress_head(logits, dv.view(B, D, 1, 1).expand(B, D, H, W).contiguous())
     prob, depth, conf, var = dm.ops.softmax_regress(logits.to(dev()), dv.to(dev()))
+    if (want["prob_volume"] - torch.softmax(logits, 1)).abs().max() > 1e-6:
+        # Seen intermittently on the GPU boxes' hosts when this runs right after the large multi-threaded CPU convolutions
+        # of test_gpu_conv_tc.py: the oracle's CPU result disagreed with torch.softmax of the same logits by 3.6e-5 while
+        # the CUDA result matched torch's softmax on the GPU bit for bit.  The oracle is the checker: recompute it and
+        # insist that it is self-consistent before judging the kernel against it.
+        want = O.regress_head(logits, hyp if per_pixel else dv.view(B, D, 1, 1).expand(B, D, H, W).contiguous())
+        assert (want["prob_volume"] - torch.softmax(logits, 1)).abs().max() <= 1e-6, "CPU oracle is not self-consistent"
     assert (prob.cpu() - want["prob_volume"]).abs().max() < 1e-6
     assert _rel(depth.cpu(), want["depth"]).max() < 2e-6
     assert ((conf.cpu() - want["photometric_confidence"]).abs() > 1e-5).float().mean() < 2e-3
