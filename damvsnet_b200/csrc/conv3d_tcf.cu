@@ -59,7 +59,7 @@ struct Params {
   const __nv_bfloat16* skip;
   void* out;
   int B, D, H, W;            // stride 1: input extents = output extents
-  int Cout, out_G, relu, plain_out, nslots, tiles_x, tiles_y, ntiles;
+  int Cout, out_G, relu, plain_out, log_nslots, tiles_x, tiles_y, ntiles;
 };
 
 __host__ __device__ constexpr int nsteps_of(int G) { return G == 1 ? 2 : 3 * (G / 2); }
@@ -78,16 +78,15 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
   extern __shared__ __align__(1024) uint8_t smem[];
   const int slot_bytes = G * R0 * kP * 16;
-  const int nslots = P.nslots;
+  const int nslots = 1 << P.log_nslots;   // 4 or 8
   uint8_t* sA = smem;
   uint8_t* sB = sA + nslots * slot_bytes;                   // [NSTEPS][2][N3][16 B]
   float* sScale = reinterpret_cast<float*>(sB + NSTEPS * 2 * N3 * 16);
   float* sShift = sScale + 16;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sShift + 16);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kMaxSlots;
-  uint64_t* acc_full = bars + 2 * kMaxSlots;
-  uint64_t* acc_empty = acc_full + RING;
+  uint64_t* full = bars;                      // TMA -> MMA: plane landed
+  uint64_t* done = bars + kMaxSlots;          // MMA -> TMA and epilogue: the iteration's MMAs have completed
+  uint64_t* acc_empty = bars + 2 * kMaxSlots; // epilogue -> MMA: accumulator slot drained and zeroed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + RING);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,8 +106,8 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
     }
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < RING; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&done[i], 1); }
+    for (int i = 0; i < RING; ++i) mbar_init(&acc_empty[i], 4);
     fence_barrier_init();
     tma_prefetch_desc(&map0);
   }
@@ -144,7 +143,7 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
       for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         TILE_COORDS(tile)
         for (int p = 0; p < D; ++p) {
-          if (round > 0) mbar_wait(&empty[slot], (round - 1) & 1);
+          if (round > 0) mbar_wait(&done[slot], (round - 1) & 1);
           mbar_arrive_expect_tx(&full[slot], (uint32_t)slot_bytes);
           tma_load_4d(sA + slot * slot_bytes, &map0, &full[slot], (tx0 - 1) * 8, ty0 - 1, p, b * G);
           if (++slot == nslots) { slot = 0; ++round; }
@@ -162,10 +161,10 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
       for (int p = 0; p < D; ++p) {
         mbar_wait(&full[slot], round & 1);
         // accumulator slots whose first contribution comes from this plane must have been drained and zeroed
+        // (at the end of a tile this is the next tile's plane 0, so a tile's first iteration need not wait again)
         {
           const long long g1 = zb + p + 1;
-          if (p + 1 < D && g1 >= RING) mbar_wait(&acc_empty[g1 & 3], (uint32_t)(((g1 >> 2) - 1) & 1));
-          if (p == 0 && zb >= RING) mbar_wait(&acc_empty[zb & 3], (uint32_t)(((zb >> 2) - 1) & 1));
+          if (g1 >= RING) mbar_wait(&acc_empty[g1 & 3], (uint32_t)(((g1 >> 2) - 1) & 1));
         }
         tc_fence_after();
         // blocks j = 0,1,2 <-> kd = 2,1,0 <-> output plane p - 1 + j; B rows are stored in this order
@@ -193,11 +192,8 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
             }
           }
         }
-        if (leader) {
-          mma_commit(&empty[slot]);                                   // the plane can be overwritten
-          if (p >= 1) mma_commit(&acc_full[(zb + p - 1) & 3]);        // output plane p - 1 is complete
-          if (p == D - 1) mma_commit(&acc_full[(zb + p) & 3]);        // ... and so is the last one
-        }
+        // one commit: the plane can be overwritten (producer), output plane p - 1 -- and D - 1 at the end -- is complete (epilogue)
+        if (leader) mma_commit(&done[slot]);
         if (++slot == nslots) { slot = 0; ++round; }
         __syncwarp();
       }
@@ -228,11 +224,12 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
         if ((int)(gz & 1) != h) continue;
         const int sl = (int)(gz & 3);
         const uint32_t tq = tmem_base + ((uint32_t)(32 * q) << 16);
+        const uint32_t g = (uint32_t)zb + min(z + 1, D - 1);   // the iteration that completes plane z
         uint4 sk[U];
 #pragma unroll
         for (int u = 0; u < U; ++u)
           sk[u] = (P.skip && valid[u / CPG] && (u % CPG) < ngroups) ? __ldg(reinterpret_cast<const uint4*>(P.skip + offs[u] + (size_t)z * z_stride)) : make_uint4(0, 0, 0, 0);
-        mbar_wait(&acc_full[sl], (uint32_t)((gz >> 2) & 1));
+        mbar_wait(&done[g & (nslots - 1)], (g >> P.log_nslots) & 1u);
         tc_fence_after();
         if (P.plain_out) {
           uint32_t y0[MC], y1[MC], y2[MC];
@@ -352,10 +349,11 @@ static int launch_g(const damvs_conv3d_desc* d, Params& P, const void* in, cudaS
                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(DAMVS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   const size_t sb = (size_t)G * R0 * kP * 16, fx = fixed_smem(G, S_::N3);
-  int nslots = (int)std::min<size_t>(kMaxSlots, ((227 * 1024) / 2 - fx - 1024) / sb);   // two CTAs per SM
-  static const int cap = getenv("DAMVS_TCF_SLOTS") ? atoi(getenv("DAMVS_TCF_SLOTS")) : 8;   // development knob
-  nslots = std::max(2, std::min(nslots, cap));
-  P.nslots = nslots;
+  // ring of 8 planes when two CTAs per SM still fit, else 4 (a power of two: the epilogue maps an iteration to its slot)
+  static const int cap = getenv("DAMVS_TCF_SLOTS") ? atoi(getenv("DAMVS_TCF_SLOTS")) : 8;   // development knob: 4 or 8
+  const size_t room = ((227 * 1024) / 2 - fx - 1024) / sb;
+  P.log_nslots = (room >= 8 && cap >= 8) ? 3 : 2;
+  const int nslots = 1 << P.log_nslots;
   const size_t smem = fx + (size_t)nslots * sb;
   auto kern = conv3d_tcf_kernel<G, CPN>;
   DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
