@@ -33,6 +33,12 @@ def main():
     ours = [(k, v) for k, v in launches.items() if klass(v["name"])]
     if len(sys.argv) > 3:          # launches of this library in ONE step (the list may hold warm-up / further steps)
         ours = ours[:int(sys.argv[3])]
+    keep = {k for k, _ in ours}
+    if src != prefix + "_launches_final.csv":   # the committed copy holds only this library's launches of that step
+        with open(prefix + "_launches_final.csv", "w", newline="") as f:
+            w = csv.writer(f, quoting=csv.QUOTE_ALL)
+            w.writerow(hdr)
+            w.writerows(r for r in rows[1:] if r[iid] in keep)
     tot_ms = sum(v.get("gpu__time_duration.sum", 0.0) for _, v in ours) / 1e6
     agg = defaultdict(lambda: {"n": 0, "ms": 0.0, "rd": 0.0, "wr": 0.0})
     with open(prefix + "_launches_final.md", "w") as f:
