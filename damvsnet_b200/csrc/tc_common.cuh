@@ -35,21 +35,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint elapses) instead
+// of re-issuing the poll -- measured on conv0 at stage 3, a quarter of all issued instructions were polls of the waiting
+// half of the epilogue warps (profiles/r01_ncu_final_summary.md), issue slots the draining half needs.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)   // ns; the hardware may cap it
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (a CUDA error the host sees) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-    if (spin > (1u << 24)) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {   // a poll lasts up to the suspend hint: 1 s .. 20 s in all
+    if (spin > (1u << 20)) {
       printf("damvs: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
       __trap();
     }
