@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
   uint64_t* empty = bars + kMaxSlots;
   uint64_t* tmem_full = bars + 2 * kMaxSlots;
   uint64_t* tmem_empty = bars + 2 * kMaxSlots + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 4);
+  uint64_t* wbar = bars + 2 * kMaxSlots + 4;   // the layer's weights have landed in shared memory
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxSlots + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile -> (batch item, tile origin); origins are output coords for S1/S2, input coords for T
@@ -245,10 +246,9 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
 
   if (threadIdx.x == 0) { TRACE(0); }
   // ---- one-time setup ------------------------------------------------------------------------
+  // The weights (up to 110 KB for the 64-channel layers) arrive by bulk copies issued below, off the critical path: the
+  // per-CTA timelines of the coarse layers showed 4.5-7 us of a 10-15 us CTA life spent in a ld.global / st.shared loop.
   {
-    const uint4* wsrc = reinterpret_cast<const uint4*>(P.blob + weights_offset(nsteps));
-    uint4* wdst = reinterpret_cast<uint4*>(sB);
-    for (int i = threadIdx.x; i < nsteps * 2 * N; i += blockDim.x) wdst[i] = __ldg(wsrc + i);
     for (int i = threadIdx.x; i < CP; i += blockDim.x) {
       int co = P.n0 + i;
       bool ok = co < P.Cout;
@@ -260,7 +260,14 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
     for (int i = 0; i < nslots; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     mbar_init(&tmem_full[0], 1); mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 8); mbar_init(&tmem_empty[1], 8);
+    mbar_init(wbar, 1);
     fence_barrier_init();
+    {
+      const uint8_t* wsrc = P.blob + weights_offset(nsteps);
+      const uint32_t wbytes = (uint32_t)nsteps * 2 * N * 16;
+      mbar_arrive_expect_tx(wbar, wbytes);
+      for (uint32_t off = 0; off < wbytes; off += 32768) bulk_load(sB + off, wsrc + off, min(32768u, wbytes - off), wbar);
+    }
     tma_prefetch_desc(&map0);
     if (MODE == MODE_S2) tma_prefetch_desc(&map1);
   }
@@ -308,6 +315,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
     const bool leader = elect_one();
     const uint32_t a_base16 = smem_u32(sA) >> 4, b_base16 = smem_u32(sB) >> 4;
     const uint32_t slot16 = (uint32_t)slot_stride >> 4;
+    mbar_wait(wbar, 0);                                      // B operand in place
     int wait_slot = 0, wait_round = 0;                       // full-barrier cursor (runs across tiles)
     int base_slot = 0;                                       // slot of the first plane of this iteration
     int acc_n = 0;                                           // accumulator buffers handed to the epilogue so far
@@ -733,7 +741,7 @@ static size_t slot_bytes(int mode, int G, int MC) {
   return (size_t)G * rows * kP * 16;
 }
 static size_t fixed_smem(int CP, int nsteps) {
-  return (size_t)nsteps * 2 * 3 * CP * 16 + 2 * CP * sizeof(float) + (2 * kMaxSlots + 4) * sizeof(uint64_t) + 16;
+  return (size_t)nsteps * 2 * 3 * CP * 16 + 2 * CP * sizeof(float) + (2 * kMaxSlots + 5) * sizeof(uint64_t) + 16;
 }
 constexpr size_t kSmemBudget = 227 * 1024;
 
