@@ -47,6 +47,13 @@ using namespace tc;
 
 constexpr int kP = 32;         // patch pitch in voxels (one TMA box row = 32 voxels * 16 B)
 constexpr int kMaxSlots = 16;  // depth-plane ring (actual depth chosen per launch)
+// Accumulator buffers in TMEM: two when they fit -- except the 16-channel transposed layers (conv9, conv11: 192 columns),
+// which run single-buffered in 256 columns so that two CTAs share an SM instead of one double-buffered CTA in 512: their
+// epilogue (8 output positions per input voxel) is the long phase, and 16 epilogue warps per SM hide its latencies better
+// than 8 (conv11 128/124/57 -> 105/108/50 us at stages 3/2/1; no change with four views in flight).
+__host__ __device__ constexpr int nbuf_of(int mode, int cp, int acc_cols) {
+  return (mode == 2 && cp == 16 && acc_cols == 192) ? 1 : (2 * acc_cols <= 512 ? 2 : 1);
+}
 constexpr int kMaxSteps = 96;
 constexpr uint32_t kMagic = 0x44544332u;  // "DTC2"
 
@@ -204,7 +211,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
   constexpr int N = 3 * CP;
   constexpr int TH = 4 * MC;
   constexpr int ACC_COLS = G_::ncls * MC * N;
-  constexpr int NBUF = 2 * ACC_COLS <= 512 ? 2 : 1;
+  constexpr int NBUF = nbuf_of(MODE, CP, ACC_COLS);
   constexpr int NEED = NBUF * ACC_COLS;
   constexpr int TMEM_COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
   static_assert(ACC_COLS <= 512, "TMEM budget");
@@ -802,7 +809,7 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   const int regs_per_cta = ((fa.numRegs + 7) / 8 * 8) * 320;
   int occ = std::min({(int)((228 * 1024) / (smem + fa.sharedSizeBytes + 1024)), 65536 / regs_per_cta, 2048 / 320});
   constexpr int ACC = Geo<MODE>::ncls * MC * 3 * CP;
-  constexpr int NEEDC = (2 * ACC <= 512 ? 2 : 1) * ACC;
+  constexpr int NEEDC = nbuf_of(MODE, CP, ACC) * ACC;
   constexpr int TCOLS = NEEDC <= 32 ? 32 : NEEDC <= 64 ? 64 : NEEDC <= 128 ? 128 : NEEDC <= 256 ? 256 : 512;
   occ = std::max(1, std::min(occ, 512 / TCOLS));
   static const int occ_cap = getenv("DAMVS_TC_OCC") ? atoi(getenv("DAMVS_TC_OCC")) : 8;   // development knob
