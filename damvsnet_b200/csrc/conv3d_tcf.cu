@@ -16,6 +16,8 @@
 //
 // Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 epilogue: the two warps of a TMEM
 // lane quarter alternate output planes, so two planes are drained concurrently while the MMAs of the next two run.
+// Barriers: full[slot] (TMA -> MMA), done[slot] (ONE tcgen05.commit per iteration: it frees the plane's slot for the
+// producer and tells the epilogue that output plane p - 1 is complete) and acc_empty[ring slot] (epilogue -> MMA).
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
