@@ -35,9 +35,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or the hint elapses) instead
-// of re-issuing the poll -- measured on conv0 at stage 3, a quarter of all issued instructions were polls of the waiting
-// half of the epilogue warps (profiles/r01_ncu_final_summary.md), issue slots the draining half needs.
+// try_wait with a suspend-time hint (the form CUTLASS uses).  Polling is not free here: on conv0 at stage 3 a quarter of
+// all issued warp instructions are polls by the waiting half of the epilogue warps.  Measured afterwards: the hint does
+// NOT change that on this hardware / driver (100.4 M warp instructions with and without it, profiles/r01_ncu_final_summary.md),
+// so the suspend time is evidently capped well below the waits seen here; kept because it is harmless.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
