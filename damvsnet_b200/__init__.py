@@ -8,7 +8,7 @@ library behind include/damvs.h (built in-tree by ``python -m damvsnet_b200.build
 from . import ops  # noqa: F401
 from .cas_mvsnet import DepthNet  # noqa: F401
 from .module import (AggWeightNetVolume, Conv3d, CostRegNet, Deconv3d, depth_regression,  # noqa: F401
-                     homo_warping, uncertainty_aware_samples)
+                     homo_warping, invalidate_packed, uncertainty_aware_samples)
 from .losses import cross_view_loss  # noqa: F401
 from .ops import G8Volume, precision, set_precision  # noqa: F401
 

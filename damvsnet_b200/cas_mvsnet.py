@@ -58,7 +58,8 @@ class DepthNet(nn.Module):
             wnet = wn.folded_with_grad() if wn is not None else None
             return ops.G8Volume(ag.WarpAggFn.apply(wnet, rot_trans, dv, self.mode, out_dtype, *nhwc))
         # bf16 pipeline: fp16 NHWC features (half the gather bytes); fp32 pipeline: exact fp32 features
-        nhwc = ops.features_to_nhwc_half_multi(features) if out_dtype == torch.bfloat16 else [ops.features_to_nhwc(f) for f in features]
+        half = out_dtype == torch.bfloat16 and ops.half_features()
+        nhwc = ops.features_to_nhwc_half_multi(features) if half else [ops.features_to_nhwc(f) for f in features]
         wnet = wn.folded() if wn is not None else None
         return ops.warp_aggregate(nhwc[0], nhwc[1:], rot_trans, depth_values, wnet, self.mode, out_dtype)
 

@@ -36,6 +36,18 @@ void count_launch();
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// SM count of the CURRENT device, cached per device ordinal (a process may drive several GPUs, e.g. DataParallel threads).
+inline int current_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return 148;
+  if (dev < 64 && cache[dev]) return cache[dev];
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  if (dev < 64) cache[dev] = n;
+  return n;
+}
+
 // ---- G8 volume addressing ---------------------------------------------------
 // element offset of channel 0 of group g at voxel (z,y,x) of batch item b
 __host__ __device__ inline size_t g8_offset(int b, int g, int z, int y, int x, int G, int D, int H, int W) {

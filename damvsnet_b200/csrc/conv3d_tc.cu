@@ -814,21 +814,24 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   occ = std::max(1, std::min(occ, 512 / TCOLS));
   static const int occ_cap = getenv("DAMVS_TC_OCC") ? atoi(getenv("DAMVS_TC_OCC")) : 8;   // development knob
   occ = std::min(occ, occ_cap);
-  static int num_sms = 0;
-  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int num_sms = current_sm_count();
   dim3 grid((unsigned)std::min(P.ntiles, occ * num_sms), 1, 1);
+#ifdef DAMVS_TC_TRACE_BUILD
+  // Development aid, compiled ONLY into a -DDAMVS_TC_TRACE_BUILD library: timestamps of a few CTAs, printed to stderr.
+  // It allocates and synchronises, which the product C ABI never does (and which would break graph capture).
   const char* tr = getenv("DAMVS_TC_TRACE");
-  if (tr) {  // development aid: timestamps of a few CTAs, printed to stderr (synchronises!)
+  if (tr) {
     const size_t n = (size_t)grid.x * 64;
-    unsigned long long* dbuf;
-    cudaMalloc(&dbuf, n * 8);
-    cudaMemset(dbuf, 0, n * 8);
+    unsigned long long* dbuf = nullptr;
+    DAMVS_CUDA_OK(cudaMalloc(&dbuf, n * 8));
+    DAMVS_CUDA_OK(cudaMemsetAsync(dbuf, 0, n * 8, st));
     P.trace = dbuf;
     kern<<<grid, 320, smem, st>>>(m0, m1, P);
-    cudaStreamSynchronize(st);
+    DAMVS_LAUNCH_OK("conv3d_tc kernel (trace)");
+    DAMVS_CUDA_OK(cudaStreamSynchronize(st));
     std::vector<unsigned long long> h(n);
-    cudaMemcpy(h.data(), dbuf, n * 8, cudaMemcpyDeviceToHost);
-    cudaFree(dbuf);
+    DAMVS_CUDA_OK(cudaMemcpy(h.data(), dbuf, n * 8, cudaMemcpyDeviceToHost));
+    DAMVS_CUDA_OK(cudaFree(dbuf));
     P.trace = nullptr;
     unsigned long long t0 = ~0ull, t1 = 0;
     for (size_t c = 0; c < n / 64; ++c) { if (h[c * 64]) t0 = std::min(t0, h[c * 64]); t1 = std::max(t1, h[c * 64 + 2]); }
@@ -845,6 +848,7 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
     }
     return DAMVS_OK;
   }
+#endif
   kern<<<grid, 320, smem, st>>>(m0, m1, P);
   DAMVS_LAUNCH_OK("conv3d_tc kernel");
   return DAMVS_OK;

@@ -301,8 +301,7 @@ int conv3d_tcp_launch(const damvs_conv3d_desc* d, const void* in, const void* pa
   P.tiles_x = (d->Win + TW - 1) / TW;
   P.tiles_y = (d->Hin + TH - 1) / TH;
   P.ntiles = P.tiles_x * P.tiles_y * d->B;
-  static int num_sms = 0;
-  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int num_sms = current_sm_count();
   static const int occ_cap = getenv("DAMVS_TC_OCC") ? atoi(getenv("DAMVS_TC_OCC")) : 2;   // development knob
   dim3 grid((unsigned)std::min(P.ntiles, std::min(2, occ_cap) * num_sms), 1, 1);
   conv3d_tcp_kernel<<<grid, THREADS, smem, st>>>(m0, P);

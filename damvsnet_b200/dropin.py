@@ -23,10 +23,15 @@ HOT_NAMES = ("homo_warping", "depth_regression", "Conv3d", "Deconv3d", "CostRegN
 _saved: Dict[str, Dict[str, object]] = {}
 
 
-def install(module_pkg: str = "models") -> List[str]:
+def install(module_pkg: str = "models", precision: str = "fp32") -> List[str]:
     """Rebind the hot-path names of ``<module_pkg>.module`` and ``<module_pkg>.cas_mvsnet``.  Returns the patched
-    qualified names.  Idempotent; ``uninstall()`` restores the reference's own definitions."""
+    qualified names.  Idempotent; ``uninstall()`` restores the reference's own definitions.
+
+    `precision` is set explicitly: "fp32" (default) keeps the reference's arithmetic width (relative depth error
+    <= 1e-4 against the reference); "bf16" opts into the reduced-precision pipeline (fp16 features, bf16 cost volume
+    and tensor-core convolutions; its error bound is stated in DESIGN.md section 5)."""
     import damvsnet_b200 as dm
+    dm.set_precision(precision)
     mod = importlib.import_module(module_pkg + ".module")
     cas = importlib.import_module(module_pkg + ".cas_mvsnet")
     patched = []

@@ -25,7 +25,29 @@ from . import ops
 from .ops import G8Volume
 
 __all__ = ["Conv3d", "Deconv3d", "CostRegNet", "AggWeightNetVolume", "homo_warping", "depth_regression",
-           "uncertainty_aware_samples"]
+           "uncertainty_aware_samples", "invalidate_packed"]
+
+# Packed-weight / folded-BatchNorm caches are keyed on (epoch, data_ptr, tensor._version) of every tensor they were
+# built from.  In-place writes through autograd-visible ops (optimizer steps, load_state_dict, copy_ under no_grad)
+# bump `_version`; module moves (`.to()`, `.cuda()`, DataParallel replication through `_apply`) bump the epoch here.
+# Writes that bypass both -- `p.data.copy_(...)`, `dist.broadcast(p.data)`, EMA swaps through `.data` -- do NOT bump
+# `_version`: call `invalidate_packed()` after them (damvsnet_b200.training.broadcast_module_state does).
+_EPOCH = [0]
+
+
+def invalidate_packed() -> None:
+    """Drop every cached packed weight / folded BatchNorm of this process (they are rebuilt on next use).  Needed only
+    after parameters or BatchNorm buffers were written through `.data` (which leaves `tensor._version` unchanged)."""
+    _EPOCH[0] += 1
+
+
+class _EpochOnApply(nn.Module):
+    """Mixin: `module._apply` (device / dtype moves, DataParallel replicas) invalidates the caches, because a moved
+    parameter can land at a recycled address with a `_version` that matches a stale cache entry."""
+
+    def _apply(self, fn, *args, **kwargs):
+        invalidate_packed()
+        return super()._apply(fn, *args, **kwargs)
 
 
 def _bn_affine(bn: nn.BatchNorm3d) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -36,10 +58,10 @@ def _bn_affine(bn: nn.BatchNorm3d) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def _versions(*tensors) -> tuple:
-    return tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
+    return (_EPOCH[0],) + tuple((t.data_ptr(), t._version) for t in tensors if t is not None)
 
 
-class _ConvBlock(nn.Module):
+class _ConvBlock(_EpochOnApply):
     """Shared machinery of Conv3d / Deconv3d: parameters as in the reference, packed-weight cache."""
 
     transposed = False
@@ -166,7 +188,7 @@ class Deconv3d(_ConvBlock):
         self._init_cache()
 
 
-class CostRegNet(nn.Module):
+class CostRegNet(_EpochOnApply):
     """3-level 3-D U-Net regulariser (reference models/module.py:510-541)."""
 
     def __init__(self, in_channels, base_channels):
@@ -237,7 +259,7 @@ class CostRegNet(nn.Module):
         return self.forward_g8(vol).unsqueeze(1)
 
 
-class AggWeightNetVolume(nn.Module):
+class AggWeightNetVolume(_EpochOnApply):
     """Per-view, per-voxel visibility weight net (reference models/module.py:544-563).
 
     Parameters mirror the reference exactly, including the dead ``conv0``.  In
@@ -287,13 +309,31 @@ class AggWeightNetVolume(nn.Module):
         return torch.cat([a.conv.weight.reshape(-1), s1, b1, b.conv.weight.reshape(-1), s2, b2]).float().contiguous()
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """Stand-alone reference signature [B,C,D,H,W] -> [B,1,D,H,W].  Not used by DepthNet (fused there);
-        evaluated with the same folded affine form the kernel uses."""
-        v = self.folded()
+        """Stand-alone reference signature [B,C,D,H,W] -> [B,1,D,H,W] (reference models/module.py:555-563).  NOT on the
+        hot path: DepthNet evaluates the weight net inside the fused warp/aggregate kernels.  This entry exists so the
+        class is a complete stand-in for the reference's: the two 1x1x1 conv + BatchNorm + ReLU blocks on C-to-1 /
+        1-to-1 channels are C- and scalar-sized per-voxel affine maps, written here with tensor ops in both modes --
+        eval(): the folded form the kernel uses; train(): batch statistics over (B,D,H,W), running buffers updated with
+        momentum 0.1 and the unbiased variance, gradients through autograd, exactly as nn.BatchNorm3d does."""
+        a, b = self.w_net[0], self.w_net[1]
         c = self.in_channels
-        s = (x * v[:c].view(1, c, 1, 1, 1)).sum(dim=1, keepdim=True)
-        a = torch.relu(s * v[c] + v[c + 1])
-        return torch.relu((a * v[c + 2]) * v[c + 3] + v[c + 4])
+        if not self.training and not ag.wants_grad(x, *self.w_net.parameters()):
+            v = self.folded()
+            s = (x * v[:c].view(1, c, 1, 1, 1)).sum(dim=1, keepdim=True)
+            h = torch.relu(s * v[c] + v[c + 1])
+            return torch.relu((h * v[c + 2]) * v[c + 3] + v[c + 4])
+        y = (x * a.conv.weight.view(1, c, 1, 1, 1)).sum(dim=1, keepdim=True)
+        for blk, pre in ((a, None), (b, b.conv.weight.view(()))):
+            if pre is not None:
+                y = y * pre
+            bn = blk.bn
+            factor = 0.0
+            if self.training and bn.track_running_stats:
+                bn.num_batches_tracked += 1                                 # nn.BatchNorm3d.forward does this first
+                factor = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
+            y = torch.relu(torch.nn.functional.batch_norm(y, bn.running_mean, bn.running_var, bn.weight, bn.bias,
+                                                          self.training, factor, bn.eps))
+        return y
 
 
 def homo_warping(src_fea: torch.Tensor, src_proj: torch.Tensor, ref_proj: torch.Tensor,
@@ -314,8 +354,9 @@ def depth_regression(p: torch.Tensor, depth_values: torch.Tensor) -> torch.Tenso
 def uncertainty_aware_samples(cur_depth: torch.Tensor, exp_var: torch.Tensor, ndepth, dtype=None, device=None, shape=None) -> torch.Tensor:
     """Reference signature (models/module.py:999): cur_depth [B,Dtot] (first stage) or [B,1,H,W], exp_var [B,1,H,W]
     -> depth hypotheses [B,D,H,W].  The [B,1,H,W] branch runs the native kernel (at the inputs' own resolution);
-    the first-stage branch is a [B,D] range broadcast over (H,W), as in the reference.  No gradient flows into
-    the samples (the reference detaches depth and variance under grad_method="detach", cas_mvsnet.py:237-239)."""
+    the first-stage branch is a [B,D] range broadcast over (H,W), as in the reference.  Under the reference's default
+    grad_method="detach" (cas_mvsnet.py:237-239) the inputs carry no gradient and the kernel runs; inputs that require
+    grad (grad_method="undetach") take a differentiable tensor-op route so that gradient path is not lost."""
     ndepth = int(ndepth)
     if cur_depth.dim() == 2:
         lo, hi = cur_depth[:, 0], cur_depth[:, -1]
@@ -325,4 +366,15 @@ def uncertainty_aware_samples(cur_depth: torch.Tensor, exp_var: torch.Tensor, nd
     if cur_depth.dim() != 4 or cur_depth.shape[1] != 1 or exp_var.shape != cur_depth.shape:
         raise ValueError("cur_depth and exp_var must be [B,1,H,W]")
     b, _, h, w = cur_depth.shape
-    return ops.stage_hypotheses(cur_depth.detach().reshape(b, h, w).float(), exp_var.detach().reshape(b, h, w).float(), ndepth, h, w, 1)
+    if ag.wants_grad(cur_depth, exp_var):
+        # grad_method != "detach" (reference models/cas_mvsnet.py:236-243): the samples carry gradient back into the
+        # previous stage's depth and variance.  Training-only side path, D small planes of element-wise math: kept on
+        # the autograd tape with tensor ops (same formula as csrc/hypotheses.cu at scale 1; models/module.py:1012-1036).
+        eps = 1e-12
+        low = -torch.minimum(cur_depth, exp_var)
+        step = (exp_var - low) / (float(ndepth) - 1.0)
+        idx = torch.arange(ndepth, device=cur_depth.device, dtype=cur_depth.dtype).view(1, ndepth, 1, 1)
+        lin = low + step * idx                                             # [B,D,H,W]
+        offset = torch.softmax(3.0 * lin / (exp_var + eps), dim=1)
+        return cur_depth + lin + eps + offset * step
+    return ops.stage_hypotheses(cur_depth.reshape(b, h, w).float(), exp_var.reshape(b, h, w).float(), ndepth, h, w, 1)

@@ -20,30 +20,40 @@ from ._lib import AGG_ADAPTIVE, AGG_VARIANCE, BF16, CONV_DIRECT, CONV_TCGEN05, F
 # --------------------------------------------------------------------------
 # precision policy
 # --------------------------------------------------------------------------
-_POLICY = {"precision": "bf16", "conv_impl": "auto"}
+# The default is the reference's own arithmetic width: fp32 (the <= 1e-4 parity mode).  The reduced-precision pipeline
+# ('bf16': fp16 features, bf16 cost volume / activations, tensor-core convolutions, fp32 accumulation) is opt-in --
+# bench.py, HotPathTrainer users and dropin.install(precision="bf16") ask for it explicitly.
+_POLICY = {"precision": "fp32", "conv_impl": "auto", "features": "auto"}
 
 
 def get_precision() -> str:
     return _POLICY["precision"]
 
 
-def set_precision(precision: str, conv_impl: str = "auto") -> None:
-    """precision: 'bf16' (cost volume and CostRegNet activations in bf16, fp32 accumulate;
-    tensor-core convolutions) or 'fp32' (everything fp32, direct convolutions: the mode
-    the <=1e-4 depth parity claim is made in).  conv_impl: 'auto' | 'direct' | 'tcgen05'."""
-    assert precision in ("bf16", "fp32") and conv_impl in ("auto", "direct", "tcgen05")
+def set_precision(precision: str, conv_impl: str = "auto", features: str = "auto") -> None:
+    """precision: 'fp32' (default: everything fp32, direct convolutions -- the mode the <=1e-4 depth parity claim is
+    made in) or 'bf16' (cost volume and CostRegNet activations in bf16, fp32 accumulate; tensor-core convolutions).
+    conv_impl: 'auto' | 'direct' | 'tcgen05'.  features: 'auto' (fp16 NHWC features in the bf16 pipeline) | 'fp32'
+    (keep the gather in fp32 even when the cost volume is emitted in bf16: the ablation row of DESIGN.md section 5)."""
+    assert precision in ("bf16", "fp32") and conv_impl in ("auto", "direct", "tcgen05") and features in ("auto", "fp32")
     _POLICY["precision"] = precision
     _POLICY["conv_impl"] = conv_impl
+    _POLICY["features"] = features
 
 
 @contextlib.contextmanager
-def precision(precision: str, conv_impl: str = "auto"):
+def precision(precision: str, conv_impl: str = "auto", features: str = "auto"):
     old = dict(_POLICY)
-    set_precision(precision, conv_impl)
+    set_precision(precision, conv_impl, features)
     try:
         yield
     finally:
         _POLICY.update(old)
+
+
+def half_features() -> bool:
+    """Whether the bf16 pipeline gathers fp16 features (its default) or stays on fp32 features (ablation)."""
+    return _POLICY["features"] == "auto"
 
 
 def volume_dtype() -> torch.dtype:
@@ -145,6 +155,8 @@ class G8Volume:
 # --------------------------------------------------------------------------
 def features_to_nhwc(x: torch.Tensor) -> torch.Tensor:
     """[B,C,H,W] fp32 -> contiguous [B,H,W,C].  Zero-copy when x is already channels_last."""
+    if isinstance(x, torch.Tensor) and x.dtype == torch.float16:
+        x = x.float()          # fp16 features handed to the fp32 pipeline: widened, never silently kept narrow
     _need(x, "feature", torch.float32, 4)
     v = x.permute(0, 2, 3, 1)
     if v.is_contiguous():
@@ -160,6 +172,10 @@ def features_to_nhwc(x: torch.Tensor) -> torch.Tensor:
 def features_to_nhwc_half(x: torch.Tensor) -> torch.Tensor:
     """[B,C,H,W] fp32 (any memory format) -> contiguous [B,H,W,C] fp16, saturating (the bf16 pipeline's feature
     format, damvs_nchw_to_nhwc_f16)."""
+    if isinstance(x, torch.Tensor) and x.dtype == torch.float16 and x.is_cuda and x.dim() == 4:
+        # already the kernel's width: zero-copy when channels_last (what HotPathRunner uploads), one permute otherwise
+        v = x.permute(0, 2, 3, 1)
+        return v if v.is_contiguous() else v.contiguous()
     _need(x, "feature", torch.float32, 4)
     b, c, h, w = x.shape
     if c % 8:

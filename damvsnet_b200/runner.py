@@ -114,14 +114,25 @@ class HotPathRunner:
 
     # ------------------------------------------------------------------ host buffers
     @staticmethod
-    def pin_stages(stages: Sequence[StageInput]) -> List[StageInput]:
-        return [([f.pin_memory() for f in feats], proj.pin_memory(), dv.pin_memory()) for feats, proj, dv in stages]
+    def pin_stages(stages: Sequence[StageInput], feature_format: str = "nchw_f32") -> List[StageInput]:
+        """Host inputs -> pinned host inputs.  feature_format "nchw_f32" keeps the reference layout; "nhwc_f16" stores
+        each feature map as an fp16 channels_last [B,C,h,w] tensor -- the width and layout the bf16 pipeline's gather
+        kernel consumes, so the upload is half the bytes and the device side is zero-copy (no repack launch)."""
+        if feature_format not in ("nchw_f32", "nhwc_f16"):
+            raise ValueError(f"unknown feature_format {feature_format!r}")
+
+        def feat(f):
+            if feature_format == "nhwc_f16":
+                f = f.clamp(-65504.0, 65504.0).to(torch.float16).contiguous(memory_format=torch.channels_last)
+            return f.pin_memory()
+        return [([feat(f) for f in feats], proj.pin_memory(), None if dv is None else dv.pin_memory()) for feats, proj, dv in stages]
 
     @staticmethod
     def h2d_bytes(stages: Sequence[StageInput]) -> int:
         n = 0
         for feats, proj, dv in stages:
-            n += sum(f.numel() * f.element_size() for f in feats) + proj.numel() * 4 + (0 if dv is None else dv.numel() * 4)
+            n += sum(f.numel() * f.element_size() for f in feats) + proj.numel() * proj.element_size() + \
+                (0 if dv is None else dv.numel() * dv.element_size())
         return n
 
     @staticmethod
@@ -153,10 +164,11 @@ class HotPathRunner:
         # set k is overwritten only after the kernels that last read it have finished
         bset = self._submits % 2
         self._submits += 1
-        shp = lambda t: None if t is None else tuple(t.shape)
-        if self._dev_in[bset] is None or [[tuple(t.shape) for t in st[0]] + [tuple(st[1].shape), shp(st[2])] for st in self._dev_in[bset]] != \
-                [[tuple(f.shape) for f in feats] + [tuple(proj.shape), shp(dv)] for feats, proj, dv in stages]:
-            self._dev_in[bset] = [([torch.empty(f.shape, dtype=f.dtype, device=dev) for f in feats],
+        shp = lambda t: None if t is None else (tuple(t.shape), t.dtype, tuple(t.stride()))
+        if self._dev_in[bset] is None or [[shp(t) for t in st[0]] + [shp(st[1]), shp(st[2])] for st in self._dev_in[bset]] != \
+                [[shp(f) for f in feats] + [shp(proj), shp(dv)] for feats, proj, dv in stages]:
+            # empty_like keeps the strides (channels_last features stay channels_last: one flat memcpy each)
+            self._dev_in[bset] = [([torch.empty_like(f, device=dev) for f in feats],
                                 torch.empty(proj.shape, dtype=proj.dtype, device=dev),
                                 None if dv is None else torch.empty(dv.shape, dtype=dv.dtype, device=dev)) for feats, proj, dv in stages]
             self._set_done[bset] = None

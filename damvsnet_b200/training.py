@@ -92,25 +92,46 @@ class OverlappedBuckets:
         self.active = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self._left: List[int] = []
         self._done: List[object] = []
+        self._handles = []
         if self.active:
             for i, b in enumerate(self.buckets):
                 for p in b.params:
-                    p.register_post_accumulate_grad_hook(lambda _p, i=i: self._ready(i))
+                    self._handles.append(p.register_post_accumulate_grad_hook(lambda _p, i=i: self._ready(i)))
         self.reset()
 
     def reset(self) -> None:
         self._left = [len(b.params) for b in self.buckets]
         self._done = [None] * len(self.buckets)
+        self._next = len(self.buckets) - 1        # collectives are issued in ONE order on every rank: last stage first
+
+    def close(self) -> None:
+        """Remove the gradient hooks (a second trainer over the same parameters would otherwise double-count)."""
+        for h in self._handles:
+            h.remove()
+        self._handles = []
+        self.active = False
+
+    def _issue_ready(self) -> None:
+        # bucket i is started only once every later bucket has been started, so ranks whose buckets complete in a
+        # different order (e.g. one rank has a parameter without gradient) still pair the same collectives
+        while self._next >= 0 and self._left[self._next] == 0:
+            self._done[self._next] = self.buckets[self._next].allreduce(self.group, async_op=True)
+            self._next -= 1
 
     def _ready(self, i: int) -> None:
         self._left[i] -= 1
-        if self._left[i] == 0:
-            self._done[i] = self.buckets[i].allreduce(self.group, async_op=True)
+        if self._left[i] < 0:
+            raise RuntimeError("OverlappedBuckets: a second backward() before finish() (gradient accumulation) is not "
+                               "supported: call finish() after every backward, or use GradientBucket.allreduce directly")
+        self._issue_ready()
 
     def finish(self) -> None:
         if self.active:
-            for i, b in enumerate(self.buckets):
-                fin = self._done[i] if self._left[i] <= 0 else b.allreduce(self.group, async_op=True)   # a parameter got no gradient
+            # buckets the hooks could not start (a parameter got no gradient on this rank) go now, in the same order
+            while self._next >= 0:
+                self._done[self._next] = self.buckets[self._next].allreduce(self.group, async_op=True)
+                self._next -= 1
+            for fin in reversed(self._done):
                 if fin is not None:
                     fin()
         self.reset()
@@ -120,9 +141,12 @@ def broadcast_module_state(modules: Sequence[torch.nn.Module], src: int = 0, gro
     """Parameters and buffers of rank `src` to every rank (DDP's construction-time sync)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return
-    for m in modules:
-        for t in list(m.parameters()) + list(m.buffers()):
-            dist.broadcast(t.data, src=src, group=group)
+    from .module import invalidate_packed
+    with torch.no_grad():
+        for m in modules:
+            for t in list(m.parameters()) + list(m.buffers()):
+                dist.broadcast(t, src=src, group=group)     # in place on the tensor itself: bumps t._version
+    invalidate_packed()                                      # belt and braces: packed-weight caches are rebuilt
 
 
 def depth_loss(outputs: Sequence[Dict[str, torch.Tensor]], depth_gt: Sequence[torch.Tensor], masks: Sequence[torch.Tensor],

@@ -4,6 +4,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import damvsnet_b200 as dm
+dm.set_precision("bf16")   # measures the reduced-precision pipeline (the package default is fp32)
 from damvsnet_b200 import synthetic
 from damvsnet_b200.runner import make_workload
 from damvsnet_b200.training import HotPathTrainer

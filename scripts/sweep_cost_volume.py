@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     args = ap.parse_args()
     import damvsnet_b200 as dm
+    dm.set_precision("bf16")   # measures the reduced-precision pipeline (the package default is fp32)
     from damvsnet_b200 import ops, synthetic
     from damvsnet_b200.runner import HotPathRunner
     torch.set_grad_enabled(False)

@@ -2,6 +2,7 @@
 import sys, torch
 sys.path.insert(0, ".")
 import damvsnet_b200 as dm
+dm.set_precision("bf16")   # measures the reduced-precision pipeline (the package default is fp32)
 from damvsnet_b200 import ops, synthetic
 from damvsnet_b200.runner import HotPathRunner
 dev = torch.device("cuda:0")

@@ -1,9 +1,12 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
 committed reference outputs.  Run on the B200 box with ``-m gpu``.
 
-Tolerances (north star): fp32 mode -- relative depth error <= 1e-4; bf16 mode
-(tensor-core convolutions, bf16 cost volume) -- teacher-forced per stage:
-depth rel p99 <= 1e-3, max <= 5e-3; confidence abs p99 <= 2e-3.
+Tolerances: fp32 mode (the package default) -- relative depth error <= 1e-4 (north star).  bf16 mode (fp16 features,
+bf16 cost volume, tcgen05 convolutions; opt-in) -- on these 64x96 fixtures, whose heads are sharpened x6 to make the
+probability volumes multi-modal, the error is stated in units of the per-pixel hypothesis span (see
+test_depthnet_bf16_within_stated_bound); the bound in relative depth (p99 <= 1e-3, max <= 5e-3) is
+checked at full size on the un-sharpened net by tests/test_gpu_fullsize.py, and DESIGN.md section 5 holds the
+per-component ablation.
 """
 import pytest
 import torch
@@ -446,6 +449,55 @@ def test_runner_host_pipeline_matches_device(dm):
             for k in ("depth", "photometric_confidence", "variance"):
                 assert torch.equal(a[k].cpu(), b[k]), k
         runner.release(t)
+
+
+def test_runner_host_pipeline_fp16_channels_last_features(dm):
+    """pin_stages(feature_format="nhwc_f16"): the host hands over fp16 channels_last features (what the gather kernel
+    consumes); the device side is zero-copy and the result is bit-identical to the bf16 pipeline fed fp32 NCHW features
+    (the repack kernel and the host conversion both round to nearest even)."""
+    from damvsnet_b200 import _lib, synthetic
+    from damvsnet_b200.runner import HotPathRunner, make_workload
+    sd = synthetic.hot_path_state_dict(seed=3)
+    runner = HotPathRunner(sd, device=dev())
+    host = make_workload(64, 96, 3, [16, 8, 8], seed=2)
+    with dm.precision("bf16"):
+        ref = runner.run_device([([f.to(dev()) for f in fs], p.to(dev()), d.to(dev())) for fs, p, d in host])
+        pinned = runner.pin_stages(host, feature_format="nhwc_f16")
+        assert pinned[0][0][0].dtype == torch.float16 and pinned[0][0][0].shape == host[0][0][0].shape
+        assert runner.h2d_bytes(pinned) < runner.h2d_bytes(host)
+        for _ in range(2):
+            n0 = _lib.launch_count()
+            t = runner.submit_host(pinned)
+            got = runner.collect(t)
+            launches = _lib.launch_count() - n0
+            for a, b in zip(ref, got):
+                for k in ("depth", "photometric_confidence", "variance"):
+                    assert torch.equal(a[k].cpu(), b[k]), k
+            runner.release(t)
+        assert launches == 3 * 13, launches          # warp + 11 convs + head per stage: no repack launch
+        with pytest.raises(ValueError):
+            runner.pin_stages(host, feature_format="nhwc_bf16")
+
+
+def test_packed_weight_cache_follows_data_writes_after_invalidate(dm):
+    """writes through `.data` do not bump tensor._version; dm.invalidate_packed() (called by
+    broadcast_module_state) makes the eval path re-pack.  Also: module moves invalidate on their own."""
+    cr = dm.CostRegNet(8, 8).eval().to(dev())
+    x = torch.randn(1, 8, 8, 16, 24, device=dev())
+    with dm.precision("bf16"), torch.no_grad():
+        y0 = cr(x).clone()
+        cr.conv0.conv.weight.data.mul_(-1.0)            # invisible to the version counter
+        cr.prob.weight.data.mul_(2.0)
+        dm.invalidate_packed()
+        y1 = cr(x).clone()
+        assert not torch.allclose(y0, y1)
+        cr.conv0.conv.weight.data.mul_(-1.0)
+        cr.prob.weight.data.mul_(0.5)
+        dm.invalidate_packed()
+        assert torch.equal(cr(x), y0)
+        with torch.no_grad():
+            cr.prob.weight.mul_(2.0)                    # visible write: no invalidate needed
+        assert not torch.allclose(cr(x), y0)
 
 
 def test_tanks_and_temples_shape_seven_views_invariants(dm):
