@@ -53,7 +53,9 @@ def parse(argv=None):
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="fp16 (default): fp16 features / cost volume / activations, tcgen05 convolutions, fp32 accumulate; "
+                         "bf16: the same in bf16 (round 1's mode); fp32: the <= 1e-4 parity mode")
     ap.add_argument("--conv-impl", default="auto", choices=["auto", "direct", "tcgen05"])
     ap.add_argument("--mode", default="adaptive", choices=["adaptive", "variance"])
     ap.add_argument("--height", type=int, default=1152)
@@ -139,8 +141,8 @@ def algorithmic_per_view(height, width, nviews, ndepths, precision, base=8):
     bytes at v bytes per element (skip-tensor re-reads and the fp32 width of the logits are NOT counted: they are waste the
     roofline fraction should show).  Head: 2*V*4 read, V*4 + 3*h*w*4 written.  FLOPs: 2*27*Cin*Cout*V_out (V_in for the
     transposed layers)."""
-    f = 2 if precision == "bf16" else 4
-    v = 2 if precision == "bf16" else 4
+    f = 4 if precision == "fp32" else 2
+    v = 4 if precision == "fp32" else 2
     out = {"warp_agg": {"bytes": 0.0, "flops": 0.0}, "conv": {"bytes": 0.0, "flops": 0.0}, "head": {"bytes": 0.0, "flops": 0.0},
            "repack": {"bytes": 0.0, "flops": 0.0}}
     b = base
@@ -148,7 +150,7 @@ def algorithmic_per_view(height, width, nviews, ndepths, precision, base=8):
         V = d * h * w
         out["warp_agg"]["bytes"] += nviews * c * h * w * f + V * 4 + c * V * v
         out["head"]["bytes"] += 2 * V * 4 + V * 4 + 3 * h * w * 4
-        out["repack"]["bytes"] += nviews * c * h * w * (4 + f) if precision == "bf16" else 0.0
+        out["repack"]["bytes"] += nviews * c * h * w * (4 + f) if precision != "fp32" else 0.0
         # (cin, cout, input-volume divisor, output-volume divisor, transposed)
         layers = [(c, b, 1, 1, 0), (b, 2 * b, 1, 8, 0), (2 * b, 2 * b, 8, 8, 0), (2 * b, 4 * b, 8, 64, 0), (4 * b, 4 * b, 64, 64, 0),
                   (4 * b, 8 * b, 64, 512, 0), (8 * b, 8 * b, 512, 512, 0), (8 * b, 4 * b, 512, 64, 1), (4 * b, 2 * b, 64, 8, 1),
@@ -565,7 +567,7 @@ def run_ours(args):
     # ---- end to end: host buffers in, host results out, copies inside the timed region
     e2e = None
     if not args.no_e2e:
-        fmt = "nhwc_f16" if args.precision == "bf16" else "nchw_f32"
+        fmt = "nhwc_f16" if args.precision != "fp32" else "nchw_f32"
         pinned = runner.pin_stages(host_stages, feature_format=fmt)
         warm = [runner.submit_host(pinned) for _ in range(3)]      # also allocates the pinned result buffers
         for t in warm:
@@ -682,20 +684,26 @@ def run_ours(args):
     if not args.no_extras:
         extras = {}
         del run_views
-        # (1) fp32 mode (the <= 1e-4 parity mode) on the same workload, rank 0 at N = 1
+        # (1) the other precision modes on the same workload, rank 0 at N = 1: fp32 (the <= 1e-4 parity mode) and the
+        #     other 2-byte pipeline (bf16 when the headline is fp16)
         if rank == 0 and world == 1:
-            try:
-                with dm.precision("fp32"):
-                    r32 = HotPathRunner(sd, mode=args.mode, device=dev)
-                    rv = make_run_views(r32, dev_stages)
-                    rv(inflight)
-                    ms32, _, _ = timed_batches(rv, max(3, min(steps, 5)), 0.0, barrier, dev, max_reps=1)
-                    extras["fp32_views_s"] = {"value": max(3, min(steps, 5)) / (ms32 / 1e3), "note": "same workload, precision fp32 "
-                                              "(fp32 features / cost volume, direct fp32 convolutions: the <= 1e-4 parity mode)"}
-                    del rv, r32
-            except Exception as exc:  # noqa: BLE001
-                extras["fp32_views_s"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-            torch.cuda.empty_cache()
+            others = [("fp32", "fp32 features / cost volume, direct fp32 convolutions: the <= 1e-4 parity mode")]
+            if args.precision != "fp32":
+                o = "bf16" if args.precision == "fp16" else "fp16"
+                others.append((o, f"fp16 features, {o} cost volume / weights / activations, tcgen05 convolutions"))
+            for prec, note in others:
+                try:
+                    with dm.precision(prec):
+                        r2 = HotPathRunner(sd, mode=args.mode, device=dev)
+                        rv = make_run_views(r2, dev_stages)
+                        rv(inflight)
+                        n2 = max(3, min(steps, 5)) if prec == "fp32" else steps
+                        ms2, _, _ = timed_batches(rv, n2, 0.0, barrier, dev, max_reps=1)
+                        extras[f"{prec}_views_s"] = {"value": n2 / (ms2 / 1e3), "note": "same workload, precision " + prec + " (" + note + ")"}
+                        del rv, r2
+                except Exception as exc:  # noqa: BLE001
+                    extras[f"{prec}_views_s"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                torch.cuda.empty_cache()
         del dev_stages, host_stages
         torch.cuda.empty_cache()
         # (2) Tanks-and-Temples shape, views sharded over the ranks (configs[2])

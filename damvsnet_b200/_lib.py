@@ -12,7 +12,7 @@ from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_longlong, c_si
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_C", "libdamvs_b200.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
 AGG_VARIANCE, AGG_ADAPTIVE = 0, 1
 CONV_DIRECT, CONV_TCGEN05 = 0, 1
 

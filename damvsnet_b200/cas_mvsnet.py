@@ -46,6 +46,8 @@ class DepthNet(nn.Module):
         batch_stats = wn is not None and wn.training
         params = tuple(wn.w_net.parameters()) if wn is not None else ()
         if batch_stats or ag.wants_grad(*features, *params):
+            if out_dtype == torch.float16:
+                raise NotImplementedError("precision 'fp16' is the inference pipeline; train in 'bf16' or 'fp32'")
             # training path: same kernels' worth of work, recorded on the autograd tape (damvsnet_b200/autograd.py)
             with torch.no_grad():
                 rot_trans = rot_trans.detach()          # the sampling grid is not differentiated (module.py:307)
@@ -58,7 +60,7 @@ class DepthNet(nn.Module):
             wnet = wn.folded_with_grad() if wn is not None else None
             return ops.G8Volume(ag.WarpAggFn.apply(wnet, rot_trans, dv, self.mode, out_dtype, *nhwc))
         # bf16 pipeline: fp16 NHWC features (half the gather bytes); fp32 pipeline: exact fp32 features
-        half = out_dtype == torch.bfloat16 and ops.half_features()
+        half = out_dtype in ops.HALF_DTYPES and ops.half_features()
         nhwc = ops.features_to_nhwc_half_multi(features) if half else [ops.features_to_nhwc(f) for f in features]
         wnet = wn.folded() if wn is not None else None
         return ops.warp_aggregate(nhwc[0], nhwc[1:], rot_trans, depth_values, wnet, self.mode, out_dtype)

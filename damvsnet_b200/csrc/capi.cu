@@ -42,8 +42,8 @@ static int check_conv_desc(const damvs_conv3d_desc* d) {
     DAMVS_REQUIRE(d->Cout > 0 && d->Cout % 8 == 0, "conv3d: Cout=%d must be a positive multiple of 8", d->Cout);
   DAMVS_REQUIRE(d->transposed == 0 || d->transposed == 1, "conv3d: transposed must be 0/1");
   DAMVS_REQUIRE(d->transposed || d->stride == 1 || d->stride == 2, "conv3d: stride=%d must be 1 or 2", d->stride);
-  DAMVS_REQUIRE(d->in_dtype == DAMVS_F32 || d->in_dtype == DAMVS_BF16, "conv3d: bad in_dtype");
-  DAMVS_REQUIRE(d->out_dtype == DAMVS_F32 || d->out_dtype == DAMVS_BF16, "conv3d: bad out_dtype");
+  DAMVS_REQUIRE(d->in_dtype == DAMVS_F32 || d->in_dtype == DAMVS_BF16 || d->in_dtype == DAMVS_F16, "conv3d: bad in_dtype");
+  DAMVS_REQUIRE(d->out_dtype == DAMVS_F32 || d->out_dtype == DAMVS_BF16 || d->out_dtype == DAMVS_F16, "conv3d: bad out_dtype");
   DAMVS_REQUIRE(d->impl == DAMVS_CONV_DIRECT || d->impl == DAMVS_CONV_TCGEN05, "conv3d: bad impl %d", d->impl);
   return DAMVS_OK;
 }

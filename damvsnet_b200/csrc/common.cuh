@@ -1,6 +1,7 @@
 // Shared helpers for the damvs_b200 kernels (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -85,6 +86,40 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// fp32 pair -> packed fp16x2, round to nearest even, saturating to +-65504 (never inf)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+__device__ __forceinline__ F8 load8(const __half* p) {
+  F8 r;
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    r.v[2 * i] = f.x;
+    r.v[2 * i + 1] = f.y;
+  }
+  return r;
+}
+
+// 2-byte element type of a reduced-precision volume and its conversions (F16 = true: IEEE half, false: bfloat16)
+template <bool F16> struct HalfT { using type = __nv_bfloat16; };
+template <> struct HalfT<true> { using type = __half; };
+template <bool F16> __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) { return F16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+// low / high element of a packed pair as fp32
+template <bool F16> __device__ __forceinline__ float unpack_lo(uint32_t w) {
+  if (F16) return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu)));
+  return __uint_as_float(w << 16);
+}
+template <bool F16> __device__ __forceinline__ float unpack_hi(uint32_t w) {
+  if (F16) return __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+  return __uint_as_float(w & 0xffff0000u);
+}
+
 __device__ __forceinline__ void store8(float* p, const F8& r) {
   reinterpret_cast<float4*>(p)[0] = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
   reinterpret_cast<float4*>(p)[1] = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
@@ -99,6 +134,21 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const F8& r) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
+__device__ __forceinline__ void store8(__half* p, const F8& r) {
+  uint4 u;
+  u.x = pack_f16x2(r.v[0], r.v[1]);
+  u.y = pack_f16x2(r.v[2], r.v[3]);
+  u.z = pack_f16x2(r.v[4], r.v[5]);
+  u.w = pack_f16x2(r.v[6], r.v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+__device__ __forceinline__ void store4(__half* p, float a, float b, float c, float d) {
+  uint2 u;
+  u.x = pack_f16x2(a, b);
+  u.y = pack_f16x2(c, d);
+  *reinterpret_cast<uint2*>(p) = u;
+}
 __device__ __forceinline__ void store4(float* p, float a, float b, float c, float d) {
   *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }

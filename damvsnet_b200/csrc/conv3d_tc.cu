@@ -67,14 +67,14 @@ struct StepSrc {
 struct PackedHeader {  // 64 bytes
   uint32_t magic;
   int32_t mode, Cin, Cout, CP, nsteps, ncls, n0;  // n0: first output channel this blob computes
-  int32_t blob_bytes, nblobs, pad[6];
+  int32_t blob_bytes, nblobs, f16, pad[5];   // f16: weights are IEEE half (1) or bfloat16 (0)
 };
 
 struct TcParams {
   const uint8_t* blob;  // PackedHeader + StepSrc[nsteps] (padded to 16 B) + weights
   const float* scale;
   const float* shift;
-  const __nv_bfloat16* skip;
+  const uint16_t* skip;  // 2-byte elements, same type (bf16 / fp16) as the output volume
   void* out;
   int B, G, Din, Hin, Win, Dout, Hout, Wout;
   int out_G, out_g0;  // output volume's group count and first group written by this launch
@@ -126,11 +126,11 @@ __device__ __forceinline__ float shfl_dn(uint32_t v, int d) { return __uint_as_f
 // run-time (uniform) values.  The order of the steps is the order build_program() emits on the host,
 // which is also the order of the packed B operands.
 // ---------------------------------------------------------------------------------------------
-template <int N, int MC>
+template <int N, int MC, bool F16>
 __device__ __forceinline__ void issue_step(bool leader, uint32_t so, uint32_t a_off16, uint32_t lbo16, uint32_t b_base16, int step,
                                            uint32_t dcol, uint32_t acc) {
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);  // SBO = 128 B, descriptor version 1
-  constexpr uint32_t IDESC = idesc_bf16_m128(N);
+  constexpr uint32_t IDESC = idesc_m128<F16>(N);
   const uint64_t bdesc = ((uint64_t)DESC_HI << 32) | ((b_base16 + step * (2 * N)) | ((uint32_t)N << 16));  // LBO = N*16 bytes
 #pragma unroll
   for (int c = 0; c < MC; ++c) {
@@ -139,7 +139,7 @@ __device__ __forceinline__ void issue_step(bool leader, uint32_t so, uint32_t a_
   }
 }
 
-template <int MODE, int CP, int MC, int G>
+template <int MODE, int CP, int MC, int G, bool F16>
 __device__ __forceinline__ void issue_iteration(bool leader, uint32_t so0, uint32_t so1, uint32_t so2, uint32_t b_base16, uint32_t dbase) {
   using G_ = Geo<MODE>;
   constexpr int N = 3 * CP;
@@ -151,14 +151,14 @@ __device__ __forceinline__ void issue_iteration(bool leader, uint32_t so0, uint3
     for (int kd = 0; kd < 3; ++kd) {
       const uint32_t so = kd == 0 ? so0 : (kd == 1 ? so1 : so2);
       if (G == 1) {  // (kh0, kh1), (kh1 with zero weights, kh2)
-        issue_step<N, MC>(leader, so, 0, kP, b_base16, step++, dbase, kd == 0 ? 0u : 1u);
-        issue_step<N, MC>(leader, so, kP, kP, b_base16, step++, dbase, 1u);
+        issue_step<N, MC, F16>(leader, so, 0, kP, b_base16, step++, dbase, kd == 0 ? 0u : 1u);
+        issue_step<N, MC, F16>(leader, so, kP, kP, b_base16, step++, dbase, 1u);
       } else {
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
           for (int gp = 0; gp < G / 2; ++gp)
-            issue_step<N, MC>(leader, so, (uint32_t)((2 * gp * R0 + kh) * kP), (uint32_t)(R0 * kP), b_base16, step++, dbase,
+            issue_step<N, MC, F16>(leader, so, (uint32_t)((2 * gp * R0 + kh) * kP), (uint32_t)(R0 * kP), b_base16, step++, dbase,
                               (kd == 0 && kh == 0 && gp == 0) ? 0u : 1u);
       }
     }
@@ -167,15 +167,15 @@ __device__ __forceinline__ void issue_iteration(bool leader, uint32_t so0, uint3
     for (int kd = 0; kd < 3; ++kd) {
       const uint32_t so = kd == 0 ? so0 : (kd == 1 ? so1 : so2);
       if (G == 1) {  // (E row, O row r), (O row r with zero weights, O row r+1)
-        issue_step<N, MC>(leader, so, 0, P0_16, b_base16, step++, dbase, kd == 0 ? 0u : 1u);
-        issue_step<N, MC>(leader, so, P0_16, kP, b_base16, step++, dbase, 1u);
+        issue_step<N, MC, F16>(leader, so, 0, P0_16, b_base16, step++, dbase, kd == 0 ? 0u : 1u);
+        issue_step<N, MC, F16>(leader, so, P0_16, kP, b_base16, step++, dbase, 1u);
       } else {
 #pragma unroll
         for (int t = 0; t < 3; ++t)  // E (kh=1), O row r (kh=0), O row r+1 (kh=2)
 #pragma unroll
           for (int gp = 0; gp < G / 2; ++gp) {
             const uint32_t off = t == 0 ? (uint32_t)(2 * gp * R0 * kP) : P0_16 + (uint32_t)((2 * gp * R1 + (t - 1)) * kP);
-            issue_step<N, MC>(leader, so, off, (uint32_t)((t == 0 ? R0 : R1) * kP), b_base16, step++, dbase,
+            issue_step<N, MC, F16>(leader, so, off, (uint32_t)((t == 0 ? R0 : R1) * kP), b_base16, step++, dbase,
                               (kd == 0 && t == 0 && gp == 0) ? 0u : 1u);
           }
       }
@@ -195,7 +195,7 @@ __device__ __forceinline__ void issue_iteration(bool leader, uint32_t so0, uint3
           for (int bq = 0; bq <= ph; ++bq)     // h taps: shift bq
 #pragma unroll
             for (int gp = 0; gp < G / 2; ++gp) {
-              issue_step<N, MC>(leader, so, (uint32_t)((2 * gp * R0 + bq) * kP), (uint32_t)(R0 * kP), b_base16, step++, dcol, first ? 0u : 1u);
+              issue_step<N, MC, F16>(leader, so, (uint32_t)((2 * gp * R0 + bq) * kP), (uint32_t)(R0 * kP), b_base16, step++, dcol, first ? 0u : 1u);
               first = false;
             }
         }
@@ -203,7 +203,7 @@ __device__ __forceinline__ void issue_iteration(bool leader, uint32_t so0, uint3
   }
 }
 
-template <int MODE, int CP, int MC, int G>
+template <int MODE, int CP, int MC, int G, bool F16>
 __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ CUtensorMap map0,
                                                         const __grid_constant__ CUtensorMap map1,
                                                         const __grid_constant__ TcParams P) {
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
   constexpr int NEED = NBUF * ACC_COLS;
   constexpr int TMEM_COLS = NEED <= 32 ? 32 : NEED <= 64 ? 64 : NEED <= 128 ? 128 : NEED <= 256 ? 256 : 512;
   static_assert(ACC_COLS <= 512, "TMEM budget");
-  constexpr uint32_t IDESC = idesc_bf16_m128(N);
+  using HT = typename HalfT<F16>::type;   // element type of the input / output / skip volumes and of the packed weights
 
   extern __shared__ __align__(1024) uint8_t smem[];
   const int patch0_bytes = G * G_::rows0(MC) * kP * 16;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
   const int nslots = P.nslots;
   const PackedHeader* hdr = reinterpret_cast<const PackedHeader*>(P.blob);
   const int nsteps = P.nsteps;
-  if (hdr->magic != kMagic || hdr->mode != MODE || hdr->CP != CP || hdr->nsteps != nsteps) {
+  if (hdr->magic != kMagic || hdr->mode != MODE || hdr->CP != CP || hdr->nsteps != nsteps || hdr->f16 != (F16 ? 1 : 0)) {
     if (threadIdx.x == 0 && blockIdx.x == 0)
       printf("damvs: packed conv weights were built for another layer type (mode %d CP %d, kernel mode %d CP %d)\n", hdr->mode, hdr->CP, MODE, CP);
     __trap();
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
       const uint32_t so0 = a_base16 + base_slot * slot16;
       const uint32_t so1 = a_base16 + s1 * slot16;
       const uint32_t so2 = a_base16 + s2 * slot16;
-      issue_iteration<MODE, CP, MC, G>(leader && !DBG(2), so0, so1, so2, b_base16, dbase);
+      issue_iteration<MODE, CP, MC, G, F16>(leader && !DBG(2), so0, so1, so2, b_base16, dbase);
       if (leader) {
         mma_commit(&tmem_full[buf]);
 #pragma unroll
@@ -464,11 +464,11 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
             bb = bb * sScale[ng * 8 + j] + sShift[ng * 8 + j];
             if (P.relu) { a = fmaxf(a, 0.f); bb = fmaxf(bb, 0.f); }
             const uint32_t w0 = s0[j >> 1], w1 = s1[j >> 1];
-            r0.v[j] = a + __uint_as_float((j & 1) ? (w0 & 0xffff0000u) : (w0 << 16));
-            r1.v[j] = bb + __uint_as_float((j & 1) ? (w1 & 0xffff0000u) : (w1 << 16));
+            r0.v[j] = a + ((j & 1) ? unpack_hi<F16>(w0) : unpack_lo<F16>(w0));
+            r1.v[j] = bb + ((j & 1) ? unpack_hi<F16>(w1) : unpack_lo<F16>(w1));
           }
           if (validT[c]) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(P.out) + offsT[u];
+            HT* o = reinterpret_cast<HT*>(P.out) + offsT[u];
             store8(o, r0);
             store8(o + 8, r1);
           }
@@ -514,9 +514,9 @@ __global__ void __launch_bounds__(320) conv3d_tc_kernel(const __grid_constant__ 
               a = a * sScale[ng * 8 + j] + sShift[ng * 8 + j];
               if (P.relu) a = fmaxf(a, 0.f);
               const uint32_t w = sw[j >> 1];
-              r.v[j] = a + __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
+              r.v[j] = a + ((j & 1) ? unpack_hi<F16>(w) : unpack_lo<F16>(w));
             }
-            if (validS[u]) store8(reinterpret_cast<__nv_bfloat16*>(P.out) + offsS[u], r);
+            if (validS[u]) store8(reinterpret_cast<HT*>(P.out) + offsS[u], r);
           }
         }
 #pragma unroll
@@ -655,8 +655,8 @@ struct PackMeta {
   StepSrc steps[kMaxSteps];
 };
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, uint8_t* __restrict__ blob, const __grid_constant__ PackMeta meta, int Cin,
-                                      int Cout, int co_end, int transposed, int CP, int n0, int nsteps) {
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(blob + weights_offset(nsteps));
+                                      int Cout, int co_end, int transposed, int CP, int n0, int nsteps, int f16) {
+  uint16_t* dst = reinterpret_cast<uint16_t*>(blob + weights_offset(nsteps));
   const int N = 3 * CP;
   int i = blockIdx.x * blockDim.x + threadIdx.x;  // over [nsteps][2][N][8]
   if (i == 0) *reinterpret_cast<PackedHeader*>(blob) = meta.hdr;
@@ -672,7 +672,7 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, uint8_t* __re
     const int tap = tap2 * 3 + kw;
     v = transposed ? w[((size_t)ci * Cout + co) * 27 + tap] : w[((size_t)co * Cin + ci) * 27 + tap];
   }
-  dst[i] = __float2bfloat16_rn(v);
+  dst[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 
 int conv3d_tc_pack(const damvs_conv3d_desc* d, const float* weight, void* packed, cudaStream_t st) {
@@ -695,12 +695,12 @@ int conv3d_tc_pack(const damvs_conv3d_desc* d, const float* weight, void* packed
     PackMeta meta{};
     PackedHeader& h = meta.hdr;
     h.magic = kMagic; h.mode = mode; h.Cin = d->Cin; h.Cout = d->Cout; h.CP = CP; h.nsteps = nsteps;
-    h.ncls = mode == MODE_T ? 4 : 1; h.n0 = k * cper; h.blob_bytes = (int)bb; h.nblobs = split;
+    h.ncls = mode == MODE_T ? 4 : 1; h.n0 = k * cper; h.blob_bytes = (int)bb; h.nblobs = split; h.f16 = d->in_dtype == DAMVS_F16 ? 1 : 0;
     for (int i = 0; i < nsteps; ++i) meta.steps[i] = steps[i];
     int total = nsteps * 2 * 3 * CP * 8;
     // the blob computes channels [n0, n0 + cper); rows beyond that are zero padding
     pack_weight_tc_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, blob, meta, d->Cin, d->Cout, (k + 1) * cper, d->transposed, CP,
-                                                              k * cper, nsteps);
+                                                              k * cper, nsteps, d->in_dtype == DAMVS_F16 ? 1 : 0);
     DAMVS_LAUNCH_OK("pack_weight_tc kernel");
   }
   return DAMVS_OK;
@@ -728,7 +728,7 @@ static CUtensorMapL2promotion l2_promotion() {
 }
 
 // G8 bf16 volume [BG][D][H][W*8] viewed with rows (row0, row0 + row_step, ...)
-static int make_map(CUtensorMap* m, const void* base, int BG, int D, int H, int W, int row0, int row_step, int box_rows, int G) {
+static int make_map(CUtensorMap* m, const void* base, int BG, int D, int H, int W, int row0, int row_step, int box_rows, int G, bool f16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(DAMVS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
   const int nrows = (H - row0 + row_step - 1) / row_step;
@@ -737,7 +737,7 @@ static int make_map(CUtensorMap* m, const void* base, int BG, int D, int H, int 
   cuuint32_t box[4] = {(cuuint32_t)kP * 8, (cuuint32_t)box_rows, 1, (cuuint32_t)G};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   void* addr = (void*)((const uint8_t*)base + (size_t)row0 * W * 16);
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, addr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_NONE, l2_promotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(DAMVS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) W=%d H=%d D=%d BG=%d rows=%d", (int)r, W, H, D, BG, box_rows);
   return DAMVS_OK;
@@ -752,7 +752,7 @@ static size_t fixed_smem(int CP, int nsteps) {
 }
 constexpr size_t kSmemBudget = 227 * 1024;
 
-template <int MODE, int CP, int MC, int G>
+template <int MODE, int CP, int MC, int G, bool F16>
 static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, const std::vector<StepSrc>& steps, cudaStream_t st) {
   using G_ = Geo<MODE>;
   const int nsteps = (int)steps.size();
@@ -760,10 +760,10 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   CUtensorMap m0, m1;
   int rc;
   if (MODE == MODE_S2) {
-    if ((rc = make_map(&m0, in, d->B * G, d->Din, d->Hin, d->Win, 0, 2, G_::rows0(MC), G))) return rc;
-    if ((rc = make_map(&m1, in, d->B * G, d->Din, d->Hin, d->Win, 1, 2, G_::rows1(MC), G))) return rc;
+    if ((rc = make_map(&m0, in, d->B * G, d->Din, d->Hin, d->Win, 0, 2, G_::rows0(MC), G, F16))) return rc;
+    if ((rc = make_map(&m1, in, d->B * G, d->Din, d->Hin, d->Win, 1, 2, G_::rows1(MC), G, F16))) return rc;
   } else {
-    if ((rc = make_map(&m0, in, d->B * G, d->Din, d->Hin, d->Win, 0, 1, G_::rows0(MC), G))) return rc;
+    if ((rc = make_map(&m0, in, d->B * G, d->Din, d->Hin, d->Win, 0, 1, G_::rows0(MC), G, F16))) return rc;
     m1 = m0;
   }
   // ring depth: TMA runs ahead of the MMAs by nslots - span planes
@@ -780,7 +780,7 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   while (nslots > G_::span + 1 && fx + (size_t)nslots * sb + 1024 > kSmemBudget / 2) --nslots;
   P.nslots = nslots;
   const size_t smem = fx + (size_t)nslots * sb;
-  auto kern = conv3d_tc_kernel<MODE, CP, MC, G>;
+  auto kern = conv3d_tc_kernel<MODE, CP, MC, G, F16>;
   DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int TH = 4 * MC;
   const int tiles_h = MODE == MODE_T ? d->Hin : P.Hout, tiles_w = MODE == MODE_T ? d->Win : P.Wout;
@@ -879,8 +879,9 @@ static int pick_mc(int mode, int G, int CP, int nsteps, int tile_rows, int tile_
 
 int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* packed, const float* scale, const float* shift,
                      const void* skip, void* out, cudaStream_t st) {
-  if (d->in_dtype != DAMVS_BF16 || (!d->plain_out && d->out_dtype != DAMVS_BF16))
-    return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: bf16 volumes only");
+  if ((d->in_dtype != DAMVS_BF16 && d->in_dtype != DAMVS_F16) || (!d->plain_out && d->out_dtype != d->in_dtype))
+    return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: bf16 or fp16 volumes only (input and output of the same type)");
+  const bool f16 = d->in_dtype == DAMVS_F16;
   if (d->plain_out && (d->transposed || d->stride != 1)) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: plain_out is stride-1 only");
   if (conv3d_tcp_supported(d)) {
     if (d->Din % 2 == 0) return conv3d_tcp_launch(d, in, packed, out, st);
@@ -897,7 +898,7 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
   const int CP = padded_c(cper);
   if (mode == MODE_T && CP > 32) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05: transposed Cout=%d > 32", d->Cout);
   TcParams P{};
-  P.scale = scale; P.shift = shift; P.skip = (const __nv_bfloat16*)skip; P.out = out;
+  P.scale = scale; P.shift = shift; P.skip = (const uint16_t*)skip; P.out = out;
   P.B = d->B; P.G = G; P.Din = d->Din; P.Hin = d->Hin; P.Win = d->Win;
   if (d->transposed) { P.Dout = 2 * d->Din; P.Hout = 2 * d->Hin; P.Wout = 2 * d->Win; P.niter = d->Din; }
   else { P.Dout = (d->Din - 1) / d->stride + 1; P.Hout = (d->Hin - 1) / d->stride + 1; P.Wout = (d->Win - 1) / d->stride + 1; P.niter = P.Dout; }
@@ -917,7 +918,8 @@ int conv3d_tc_launch(const damvs_conv3d_desc* d, const void* in, const void* pac
     P.n0 = k * cper; P.out_g0 = (k * cper) / 8; P.Cout = d->plain_out ? 1 : (k + 1) * cper;
     int rc = -1;
 #define GO(MODE_, CP_, MC_, G_)                                   \
-  if (mode == MODE_ && CP == CP_ && mc == MC_ && G == G_) rc = launch_one<MODE_, CP_, MC_, G_>(d, P, in, steps, st)
+  if (mode == MODE_ && CP == CP_ && mc == MC_ && G == G_)         \
+    rc = f16 ? launch_one<MODE_, CP_, MC_, G_, true>(d, P, in, steps, st) : launch_one<MODE_, CP_, MC_, G_, false>(d, P, in, steps, st)
     // the layer shapes of CostRegNet with base_channels 8 (reference models/module.py:513-530)
     GO(MODE_S1, 16, 2, 1); GO(MODE_S1, 16, 1, 1);   // conv0 (stage 3), prob
     GO(MODE_S1, 16, 2, 2); GO(MODE_S1, 16, 1, 2);   // conv0 (stage 2), conv2

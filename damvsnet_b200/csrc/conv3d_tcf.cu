@@ -58,7 +58,7 @@ struct Params {
   const uint8_t* blob;
   const float* scale;
   const float* shift;
-  const __nv_bfloat16* skip;
+  const uint16_t* skip;   // 2-byte elements, same type (bf16 / fp16) as the output volume
   void* out;
   int B, D, H, W;            // stride 1: input extents = output extents
   int Cout, out_G, relu, plain_out, log_nslots, tiles_x, tiles_y, ntiles;
@@ -72,9 +72,10 @@ __device__ __forceinline__ void tmem_st8_zero(uint32_t taddr) {
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float shfl_dn(uint32_t v, int d) { return __uint_as_float(__shfl_down_sync(0xffffffffu, v, d)); }
 
-template <int G, int CPN>
+template <int G, int CPN, bool F16>
 __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ Params P) {
   using S_ = Shape<CPN>;
+  using HT = typename HalfT<F16>::type;
   constexpr int NB = S_::NB, N3 = S_::N3, MC = S_::MC, R0 = S_::R0, TH = S_::TH, CP = CPN;
   constexpr int NSTEPS = nsteps_of(G);
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Header* hdr = reinterpret_cast<const Header*>(P.blob);
-  if (hdr->magic != kMagicF || hdr->nsteps != NSTEPS || hdr->pad[0] != CPN) {
+  if (hdr->magic != kMagicF || hdr->nsteps != NSTEPS || hdr->pad[0] != CPN || hdr->pad[1] != (F16 ? 1 : 0)) {
     if (threadIdx.x == 0 && blockIdx.x == 0) printf("damvs: packed conv weights were not built for the depth-folded kernel\n");
     __trap();
   }
@@ -186,7 +187,7 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
             if (len == 0) continue;
             const int jb = r == 0 ? j0 : j0 + run1, sl = r == 0 ? s0 : 0;
             const uint64_t bdesc = ((uint64_t)DESC_HI << 32) | ((bstep16 + jb * NB) | ((uint32_t)N3 << 16));   // LBO = N3 * 16 B
-            const uint32_t idesc = len == 3 ? idesc_bf16_m128(N3) : (len == 2 ? idesc_bf16_m128(2 * NB) : idesc_bf16_m128(NB));
+            const uint32_t idesc = len == 3 ? idesc_m128<F16>(N3) : (len == 2 ? idesc_m128<F16>(2 * NB) : idesc_m128<F16>(NB));
 #pragma unroll
             for (int c = 0; c < MC; ++c) {
               const uint64_t adesc = ((uint64_t)DESC_HI << 32) | ((so + a_off16 + c * 128) | (lbo16 << 16));
@@ -272,9 +273,9 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
               a = a * sScale[ng * 8 + j] + sShift[ng * 8 + j];
               if (P.relu) a = fmaxf(a, 0.f);
               const uint32_t w = sw[j >> 1];
-              r.v[j] = a + __uint_as_float((j & 1) ? (w & 0xffff0000u) : (w << 16));
+              r.v[j] = a + ((j & 1) ? unpack_hi<F16>(w) : unpack_lo<F16>(w));
             }
-            if (valid[u / CPG]) store8(reinterpret_cast<__nv_bfloat16*>(P.out) + offs[u] + (size_t)z * z_stride, r);
+            if (valid[u / CPG]) store8(reinterpret_cast<HT*>(P.out) + offs[u] + (size_t)z * z_stride, r);
           }
         }
         // hand the slot back zeroed: the next plane that lands in it accumulates from zero
@@ -300,9 +301,9 @@ __global__ void __launch_bounds__(320) conv3d_tcf_kernel(const __grid_constant__
 
 // B operand of step st: [2 K-halves][N3 rows][8 channels] bf16; row n = j * 48 + kw * 16 + co with j = 2 - kd.
 __global__ void pack_weight_tcf_kernel(const float* __restrict__ w, uint8_t* __restrict__ blob, const __grid_constant__ Header hdr, int Cin, int Cout,
-                                       int G, int nsteps, int CP, int NB) {
+                                       int G, int nsteps, int CP, int NB, int f16) {
   const int N3 = 3 * NB;
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(blob + sizeof(Header));
+  uint16_t* dst = reinterpret_cast<uint16_t*>(blob + sizeof(Header));
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [nsteps][2][N3][8]
   if (i == 0) *reinterpret_cast<Header*>(blob) = hdr;     // by-value argument: no staging copy, no synchronisation
   if (i >= nsteps * 2 * N3 * 8) return;
@@ -315,7 +316,7 @@ __global__ void pack_weight_tcf_kernel(const float* __restrict__ w, uint8_t* __r
   const int ci = g * 8 + j8;
   float v = 0.f;
   if (!zero && kw < 3 && co < Cout) v = w[((size_t)co * Cin + ci) * 27 + (kd * 3 + kh) * 3 + kw];
-  dst[i] = __float2bfloat16_rn(v);
+  dst[i] = f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -336,7 +337,7 @@ static EncodeTiledFn encode_fn() {
 static int cpn_of(const damvs_conv3d_desc* d) { return (d->plain_out || d->Cout <= 8) ? 8 : 16; }
 static size_t fixed_smem(int G, int N3) { return (size_t)nsteps_of(G) * 2 * N3 * 16 + 2 * 16 * sizeof(float) + (2 * kMaxSlots + 2 * RING) * sizeof(uint64_t) + 16; }
 
-template <int G, int CPN>
+template <int G, int CPN, bool F16>
 static int launch_g(const damvs_conv3d_desc* d, Params& P, const void* in, cudaStream_t st) {
   using S_ = Shape<CPN>;
   constexpr int R0 = S_::R0, TH = S_::TH;
@@ -347,8 +348,8 @@ static int launch_g(const damvs_conv3d_desc* d, Params& P, const void* in, cudaS
   cuuint64_t strides[3] = {(cuuint64_t)d->Win * 16, (cuuint64_t)d->Hin * d->Win * 16, (cuuint64_t)d->Din * d->Hin * d->Win * 16};
   cuuint32_t box[4] = {(cuuint32_t)kP * 8, (cuuint32_t)R0, 1, (cuuint32_t)G};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(&m0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(&m0, F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(DAMVS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   const size_t sb = (size_t)G * R0 * kP * 16, fx = fixed_smem(G, S_::N3);
   // ring of 8 planes when two CTAs per SM still fit, else 4 (a power of two: the epilogue maps an iteration to its slot)
@@ -357,7 +358,7 @@ static int launch_g(const damvs_conv3d_desc* d, Params& P, const void* in, cudaS
   P.log_nslots = (room >= 8 && cap >= 8) ? 3 : 2;
   const int nslots = 1 << P.log_nslots;
   const size_t smem = fx + (size_t)nslots * sb;
-  auto kern = conv3d_tcf_kernel<G, CPN>;
+  auto kern = conv3d_tcf_kernel<G, CPN, F16>;
   DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   P.tiles_x = (d->Win + TW - 1) / TW;
@@ -390,9 +391,10 @@ int conv3d_tcf_pack(const damvs_conv3d_desc* d, const float* weight, void* packe
   const int G = d->Cin / 8, nsteps = tcf::nsteps_of(G);
   tcf::Header h{};
   const int cpn = tcf::cpn_of(d), nb = cpn == 8 ? tcf::Shape<8>::NB : tcf::Shape<16>::NB;
-  h.magic = tcf::kMagicF; h.Cin = d->Cin; h.Cout = d->Cout; h.nsteps = nsteps; h.pad[0] = cpn;
+  h.magic = tcf::kMagicF; h.Cin = d->Cin; h.Cout = d->Cout; h.nsteps = nsteps; h.pad[0] = cpn; h.pad[1] = d->in_dtype == DAMVS_F16 ? 1 : 0;
   const int total = nsteps * 2 * 3 * nb * 8;
-  tcf::pack_weight_tcf_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, (uint8_t*)packed, h, d->Cin, d->plain_out ? 1 : d->Cout, G, nsteps, cpn, nb);
+  tcf::pack_weight_tcf_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, (uint8_t*)packed, h, d->Cin, d->plain_out ? 1 : d->Cout, G, nsteps, cpn, nb,
+                                                                   d->in_dtype == DAMVS_F16 ? 1 : 0);
   DAMVS_LAUNCH_OK("pack_weight_tcf kernel");
   return DAMVS_OK;
 }
@@ -400,19 +402,22 @@ int conv3d_tcf_pack(const damvs_conv3d_desc* d, const float* weight, void* packe
 int conv3d_tcf_launch(const damvs_conv3d_desc* d, const void* in, const void* packed, const float* scale, const float* shift,
                       const void* skip, void* out, cudaStream_t st) {
   tcf::Params P{};
-  P.blob = (const uint8_t*)packed; P.scale = scale; P.shift = shift; P.skip = (const __nv_bfloat16*)skip; P.out = out;
+  P.blob = (const uint8_t*)packed; P.scale = scale; P.shift = shift; P.skip = (const uint16_t*)skip; P.out = out;
   P.B = d->B; P.D = d->Din; P.H = d->Hin; P.W = d->Win;
   P.Cout = d->plain_out ? 1 : d->Cout; P.out_G = d->plain_out ? 1 : (d->Cout + 7) / 8; P.relu = d->relu; P.plain_out = d->plain_out;
   const int G = d->Cin / 8;
+  const bool f16 = d->in_dtype == DAMVS_F16;
+#define GO(G_, CPN_) return f16 ? tcf::launch_g<G_, CPN_, true>(d, P, in, st) : tcf::launch_g<G_, CPN_, false>(d, P, in, st)
   if (tcf::cpn_of(d) == 8) {
-    if (G == 1) return tcf::launch_g<1, 8>(d, P, in, st);
-    if (G == 2) return tcf::launch_g<2, 8>(d, P, in, st);
-    if (G == 4) return tcf::launch_g<4, 8>(d, P, in, st);
+    if (G == 1) GO(1, 8);
+    if (G == 2) GO(2, 8);
+    if (G == 4) GO(4, 8);
   } else {
-    if (G == 1) return tcf::launch_g<1, 16>(d, P, in, st);
-    if (G == 2) return tcf::launch_g<2, 16>(d, P, in, st);
-    if (G == 4) return tcf::launch_g<4, 16>(d, P, in, st);
+    if (G == 1) GO(1, 16);
+    if (G == 2) GO(2, 16);
+    if (G == 4) GO(4, 16);
   }
+#undef GO
   return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d tcgen05 (depth-folded): Cin=%d not supported", d->Cin);
 }
 

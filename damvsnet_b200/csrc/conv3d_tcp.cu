@@ -57,6 +57,7 @@ struct Params {
   float* out;
   int B, D, H, W;
   int tiles_x, tiles_y, ntiles, dbg;
+  uint32_t fmt_xor;   // 0 for bf16 operands; the A / B format bits of the instruction descriptor for fp16 (XOR turns them off)
 };
 
 __device__ __forceinline__ float shfl_dn(uint32_t v, int d) { return __uint_as_float(__shfl_down_sync(0xffffffffu, v, d)); }
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv3d_tcp_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Header* hdr = reinterpret_cast<const Header*>(P.blob);
-  if (hdr->magic != kMagicP) {
+  if (hdr->magic != kMagicP || hdr->pad[0] != (P.fmt_xor ? 1 : 0)) {   // wrong layer type, or weights packed for the other 2-byte format
     if (threadIdx.x == 0 && blockIdx.x == 0) printf("damvs: packed conv weights were not built for the prob kernel\n");
     __trap();
   }
@@ -152,9 +153,9 @@ __global__ void __launch_bounds__(THREADS, 2) conv3d_tcp_kernel(const __grid_con
               const uint64_t adesc = ((uint64_t)DESC_HI << 32) | (alo + c * 128);
               // a tile's first pair only touches plane 0 (block 1), and starts it
               mma_bf16_ss(d_old + c * (RING * NBP) + (first ? NBP : 0), adesc, ((uint64_t)DESC_HI << 32) | (blo + (first ? NBP : 0)),
-                          idesc_bf16_m128(first ? NBP : 2 * NBP), first ? 0u : 1u);
+                          idesc_bf16_m128(first ? NBP : 2 * NBP) ^ P.fmt_xor, first ? 0u : 1u);
               // its last pair only touches plane D - 1 (block 2)
-              mma_bf16_ss(d_new + c * (RING * NBP), adesc, ((uint64_t)DESC_HI << 32) | (blo + 2 * NBP), idesc_bf16_m128(last ? NBP : 2 * NBP), 0u);
+              mma_bf16_ss(d_new + c * (RING * NBP), adesc, ((uint64_t)DESC_HI << 32) | (blo + 2 * NBP), idesc_bf16_m128(last ? NBP : 2 * NBP) ^ P.fmt_xor, 0u);
             }
           }
           mma_commit(&done[slot]);   // the plane pair can be overwritten; output planes 2i - 1, 2i (and D - 1 at the end) are complete
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv3d_tcp_kernel(const __grid_con
 // B operand: [2 planes of the pair][64 rows][8 channels] bf16; row n = j * 16 + kh * 3 + kw for output plane 2i - 1 + j,
 // whose depth tap is kd = 2 - j for the first plane of the pair and 3 - j for the second.
 __global__ void pack_weight_tcp_kernel(const float* __restrict__ w, uint8_t* __restrict__ blob, const __grid_constant__ Header hdr) {
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(blob + sizeof(Header));
+  uint16_t* dst = reinterpret_cast<uint16_t*>(blob + sizeof(Header));
   const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over [2][64][8]
   if (i == 0) *reinterpret_cast<Header*>(blob) = hdr;
   if (i >= 2 * B_ROWS * 8) return;
@@ -239,7 +240,7 @@ __global__ void pack_weight_tcp_kernel(const float* __restrict__ w, uint8_t* __r
   const int j = n / NBP, t = n % NBP, kd = 2 + hh - j;
   float v = 0.f;
   if (t < 9 && kd >= 0 && kd < 3) v = w[(size_t)ci * 27 + kd * 9 + t];
-  dst[i] = __float2bfloat16_rn(v);
+  dst[i] = hdr.pad[0] ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -271,7 +272,7 @@ size_t conv3d_tcp_packed_bytes(const damvs_conv3d_desc*) { return (sizeof(tcp::H
 
 int conv3d_tcp_pack(const damvs_conv3d_desc* d, const float* weight, void* packed, cudaStream_t st) {
   tcp::Header h{};
-  h.magic = tcp::kMagicP; h.Cin = d->Cin;
+  h.magic = tcp::kMagicP; h.Cin = d->Cin; h.pad[0] = d->in_dtype == DAMVS_F16 ? 1 : 0;
   const int total = 2 * tcp::B_ROWS * 8;
   tcp::pack_weight_tcp_kernel<<<(total + 255) / 256, 256, 0, st>>>(weight, (uint8_t*)packed, h);
   DAMVS_LAUNCH_OK("pack_weight_tcp kernel");
@@ -290,8 +291,10 @@ int conv3d_tcp_launch(const damvs_conv3d_desc* d, const void* in, const void* pa
   cuuint64_t strides[3] = {(cuuint64_t)d->Win * 16, (cuuint64_t)d->Hin * d->Win * 16, (cuuint64_t)d->Din * d->Hin * d->Win * 16};
   cuuint32_t box[4] = {(cuuint32_t)kP * 8, (cuuint32_t)R0, 2, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(&m0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const bool f16 = d->in_dtype == DAMVS_F16;
+  P.fmt_xor = f16 ? ((1u << 7) | (1u << 10)) : 0u;
+  CUresult r = fn(&m0, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(DAMVS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   const size_t smem = kSmem;
   DAMVS_CUDA_OK(cudaFuncSetAttribute(conv3d_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

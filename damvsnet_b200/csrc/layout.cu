@@ -127,6 +127,8 @@ extern "C" int damvs_ncdhw_to_g8(const float* in, void* out, int dtype, int B, i
     ncdhw_to_g8_kernel<float><<<grid, kTilePix, 0, (cudaStream_t)stream>>>(in, (float*)out, G, V);
   else if (dtype == DAMVS_BF16)
     ncdhw_to_g8_kernel<__nv_bfloat16><<<grid, kTilePix, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, G, V);
+  else if (dtype == DAMVS_F16)
+    ncdhw_to_g8_kernel<__half><<<grid, kTilePix, 0, (cudaStream_t)stream>>>(in, (__half*)out, G, V);
   else
     return set_error(DAMVS_ERR_INVALID, "ncdhw_to_g8: bad dtype %d", dtype);
   DAMVS_LAUNCH_OK("ncdhw_to_g8");
@@ -145,6 +147,8 @@ extern "C" int damvs_g8_to_ncdhw(const void* in, int dtype, float* out, int B, i
     g8_to_ncdhw_kernel<float><<<grid, kTilePix, 0, (cudaStream_t)stream>>>((const float*)in, out, G, V);
   else if (dtype == DAMVS_BF16)
     g8_to_ncdhw_kernel<__nv_bfloat16><<<grid, kTilePix, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, out, G, V);
+  else if (dtype == DAMVS_F16)
+    g8_to_ncdhw_kernel<__half><<<grid, kTilePix, 0, (cudaStream_t)stream>>>((const __half*)in, out, G, V);
   else
     return set_error(DAMVS_ERR_INVALID, "g8_to_ncdhw: bad dtype %d", dtype);
   DAMVS_LAUNCH_OK("g8_to_ncdhw");

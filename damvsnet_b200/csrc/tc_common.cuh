@@ -106,6 +106,10 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes,
 __host__ __device__ constexpr uint32_t idesc_bf16_m128(uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
+// the same with fp16 operands (A / B format fields = 0) when F16, bf16 otherwise
+template <bool F16> __host__ __device__ constexpr uint32_t idesc_m128(uint32_t n) {
+  return F16 ? ((1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24)) : idesc_bf16_m128(n);
+}
 
 __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(

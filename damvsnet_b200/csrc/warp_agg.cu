@@ -373,6 +373,8 @@ static int launch_warp_agg(const WarpAggParams& P, int out_dtype, cudaStream_t s
   dim3 grid((P.W + TW - 1) / TW, (P.H + TH - 1) / TH, P.B);
   if (out_dtype == DAMVS_F32)
     warp_agg_kernel<C, MODE, float, DCH, false><<<grid, 128, 0, st>>>(P);
+  else if (out_dtype == DAMVS_F16)
+    warp_agg_kernel<C, MODE, __half, DCH, false><<<grid, 128, 0, st>>>(P);
   else
     warp_agg_kernel<C, MODE, __nv_bfloat16, DCH, false><<<grid, 128, 0, st>>>(P);
   DAMVS_LAUNCH_OK("warp_agg kernel");
@@ -393,7 +395,7 @@ extern "C" int damvs_warp_agg_fwd(const float* ref_nhwc, const float* const* src
   DAMVS_REQUIRE(B <= 65535, "warp_agg: B too large");
   DAMVS_REQUIRE(mode == DAMVS_AGG_VARIANCE || mode == DAMVS_AGG_ADAPTIVE, "warp_agg: bad mode %d", mode);
   DAMVS_REQUIRE(mode == DAMVS_AGG_VARIANCE || wnet != nullptr, "warp_agg: adaptive mode needs wnet");
-  DAMVS_REQUIRE(out_dtype == DAMVS_F32 || out_dtype == DAMVS_BF16, "warp_agg: bad out_dtype %d", out_dtype);
+  DAMVS_REQUIRE(out_dtype == DAMVS_F32 || out_dtype == DAMVS_BF16 || out_dtype == DAMVS_F16, "warp_agg: bad out_dtype %d", out_dtype);
   DAMVS_REQUIRE((reinterpret_cast<uintptr_t>(ref_nhwc) & 31u) == 0 && aligned16(out_vol), "warp_agg: ref must be 32-byte, out 16-byte aligned");
   WarpAggParams P;
   P.ref = ref_nhwc;

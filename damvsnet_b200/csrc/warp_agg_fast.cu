@@ -360,6 +360,8 @@ static int launch_h_cfg(const WarpAggHParams& P, int out_dtype, cudaStream_t st)
   dim3 grid((P.W + TW - 1) / TW, (P.H + TH - 1) / TH, P.B);
   const bool full = P.D % DCH == 0;
   if (out_dtype == DAMVS_F32) warp_agg_h_kernel<C, CPT, MODE, float, DCH, false, 1, false><<<grid, 128, 0, st>>>(P);
+  else if (out_dtype == DAMVS_F16 && full) warp_agg_h_kernel<C, CPT, MODE, __half, DCH, false, MINB, true><<<grid, 128, 0, st>>>(P);
+  else if (out_dtype == DAMVS_F16) warp_agg_h_kernel<C, CPT, MODE, __half, DCH, false, MINB, false><<<grid, 128, 0, st>>>(P);
   else if (full) warp_agg_h_kernel<C, CPT, MODE, __nv_bfloat16, DCH, false, MINB, true><<<grid, 128, 0, st>>>(P);
   else warp_agg_h_kernel<C, CPT, MODE, __nv_bfloat16, DCH, false, MINB, false><<<grid, 128, 0, st>>>(P);
   DAMVS_LAUNCH_OK("warp_agg_h kernel");
@@ -413,7 +415,7 @@ extern "C" int damvs_warp_agg_fwd_f16(const void* ref_nhwc, const void* const* s
   DAMVS_REQUIRE((long long)H * W * C * 2 < (1ll << 31), "warp_agg_f16: feature map too large for 32-bit tap offsets");
   DAMVS_REQUIRE(mode == DAMVS_AGG_VARIANCE || mode == DAMVS_AGG_ADAPTIVE, "warp_agg_f16: bad mode %d", mode);
   DAMVS_REQUIRE(mode == DAMVS_AGG_VARIANCE || wnet != nullptr, "warp_agg_f16: adaptive mode needs wnet");
-  DAMVS_REQUIRE(out_dtype == DAMVS_F32 || out_dtype == DAMVS_BF16, "warp_agg_f16: bad out_dtype %d", out_dtype);
+  DAMVS_REQUIRE(out_dtype == DAMVS_F32 || out_dtype == DAMVS_BF16 || out_dtype == DAMVS_F16, "warp_agg_f16: bad out_dtype %d", out_dtype);
   DAMVS_REQUIRE(aligned16(ref_nhwc) && aligned16(out_vol), "warp_agg_f16: ref and out must be 16-byte aligned");
   WarpAggHParams P;
   P.ref = (const __half*)ref_nhwc;

@@ -98,17 +98,18 @@ class _ConvBlock(_EpochOnApply):
             return ops.conv3d_pack_weight(wd.transpose(0, 1).flip(2, 3, 4).contiguous(), cout, cin, False, impl, 1)
         return self._cached(("adj", impl, w.device), _versions(w), make)
 
-    def prepared(self, impl: int):
-        """(packed weight, scale, shift) for `impl` on the parameters' device, rebuilt when they change."""
+    def prepared(self, impl: int, dtype: torch.dtype = torch.bfloat16):
+        """(packed weight, scale, shift) for `impl` and volumes of `dtype` on the parameters' device, rebuilt when they
+        change (the tcgen05 kernels hold the weights in the volumes' 2-byte type)."""
         w = self.conv.weight
         bn = self.bn
-        key = (impl, w.device)
+        key = (impl, w.device, dtype if dtype in ops.HALF_DTYPES else None)
         ver = _versions(w, *( (bn.weight, bn.bias, bn.running_mean, bn.running_var) if bn is not None else () ))
         hit = self._packed.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
         cin, cout = self.in_channels, self.out_channels
-        packed = ops.conv3d_pack_weight(w.detach().float(), cin, cout, self.transposed, impl, self.stride)
+        packed = ops.conv3d_pack_weight(w.detach().float(), cin, cout, self.transposed, impl, self.stride, dtype)
         if bn is not None:
             scale, shift = _bn_affine(bn)
         elif self.conv.bias is not None:
@@ -128,13 +129,15 @@ class _ConvBlock(_EpochOnApply):
         batch_stats = bn is not None and (self.training or not bn.track_running_stats)
         params = (self.conv.weight,) + ((bn.weight, bn.bias) if bn is not None else ())
         if batch_stats or ag.wants_grad(vol.data, None if skip is None else skip.data, *params):
+            if vol.dtype == torch.float16:
+                raise NotImplementedError("precision 'fp16' is the inference pipeline; train in 'bf16' or 'fp32'")
             if out_dtype is not None and out_dtype != vol.dtype:
                 raise NotImplementedError("training path keeps one volume dtype")
             out = ag.ConvBlockFn.apply(vol.data, None if skip is None else skip.data, self.conv.weight,
                                        None if bn is None else bn.weight, None if bn is None else bn.bias, self)
             return G8Volume(out)
         impl = ops.conv_impl_for(self.in_channels, self.out_channels, self.stride, self.transposed)
-        packed, scale, shift = self.prepared(impl)
+        packed, scale, shift = self.prepared(impl, vol.dtype)
         return ops.conv3d(vol, packed, scale, shift, self.out_channels, self.stride, self.transposed, self.relu, skip,
                           out_dtype or vol.dtype, False, impl)
 
@@ -208,14 +211,14 @@ class CostRegNet(_EpochOnApply):
         self.base_channels = base_channels
         self._prob_packed: Dict[tuple, tuple] = {}
 
-    def _prob_prepared(self, impl: int) -> torch.Tensor:
+    def _prob_prepared(self, impl: int, dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
         w = self.prob.weight
-        key = (impl, w.device)
+        key = (impl, w.device, dtype if dtype in ops.HALF_DTYPES else None)
         ver = _versions(w)
         hit = self._prob_packed.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
-        packed = ops.conv3d_pack_weight(w.detach().float(), self.base_channels, 1, False, impl)
+        packed = ops.conv3d_pack_weight(w.detach().float(), self.base_channels, 1, False, impl, 1, dtype)
         self._prob_packed[key] = (ver, packed)
         return packed
 
@@ -251,7 +254,7 @@ class CostRegNet(_EpochOnApply):
         if ag.wants_grad(x.data, self.prob.weight):
             return ag.ProbConvFn.apply(x.data, self.prob.weight, self)
         impl = ops.conv_impl_for(self.base_channels, 1, 1, False)
-        return ops.conv3d(x, self._prob_prepared(impl), None, None, 1, 1, False, False, None, torch.float32, True, impl)
+        return ops.conv3d(x, self._prob_prepared(impl, x.dtype), None, None, 1, 1, False, False, None, torch.float32, True, impl)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """Reference call signature: [B,C,D,H,W] -> [B,1,D,H,W]."""

@@ -15,14 +15,16 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import AGG_ADAPTIVE, AGG_VARIANCE, BF16, CONV_DIRECT, CONV_TCGEN05, F32, ConvDesc
+from ._lib import AGG_ADAPTIVE, AGG_VARIANCE, BF16, CONV_DIRECT, CONV_TCGEN05, F16, F32, ConvDesc
 
 # --------------------------------------------------------------------------
 # precision policy
 # --------------------------------------------------------------------------
-# The default is the reference's own arithmetic width: fp32 (the <= 1e-4 parity mode).  The reduced-precision pipeline
-# ('bf16': fp16 features, bf16 cost volume / activations, tensor-core convolutions, fp32 accumulation) is opt-in --
-# bench.py, HotPathTrainer users and dropin.install(precision="bf16") ask for it explicitly.
+# The default is the reference's own arithmetic width: fp32 (the <= 1e-4 parity mode).  The reduced-precision pipelines
+# are opt-in -- bench.py, HotPathTrainer users and dropin.install(precision=...) ask for them explicitly:
+#   'fp16'  fp16 features, fp16 cost volume / activations / weights, tcgen05 convolutions, fp32 accumulation.  Inference.
+#           11 significand bits: 8x finer than bf16 at the same width and tensor-core rate.
+#   'bf16'  the same with bf16 volumes / activations / weights: the exponent range training gradients need.
 _POLICY = {"precision": "fp32", "conv_impl": "auto", "features": "auto"}
 
 
@@ -32,10 +34,11 @@ def get_precision() -> str:
 
 def set_precision(precision: str, conv_impl: str = "auto", features: str = "auto") -> None:
     """precision: 'fp32' (default: everything fp32, direct convolutions -- the mode the <=1e-4 depth parity claim is
-    made in) or 'bf16' (cost volume and CostRegNet activations in bf16, fp32 accumulate; tensor-core convolutions).
+    made in), 'fp16' or 'bf16' (cost volume and CostRegNet activations / weights in that 2-byte type, fp32 accumulate;
+    tensor-core convolutions; fp16 is inference-only).
     conv_impl: 'auto' | 'direct' | 'tcgen05'.  features: 'auto' (fp16 NHWC features in the bf16 pipeline) | 'fp32'
     (keep the gather in fp32 even when the cost volume is emitted in bf16: the ablation row of DESIGN.md section 5)."""
-    assert precision in ("bf16", "fp32") and conv_impl in ("auto", "direct", "tcgen05") and features in ("auto", "fp32")
+    assert precision in ("bf16", "fp16", "fp32") and conv_impl in ("auto", "direct", "tcgen05") and features in ("auto", "fp32")
     _POLICY["precision"] = precision
     _POLICY["conv_impl"] = conv_impl
     _POLICY["features"] = features
@@ -56,8 +59,12 @@ def half_features() -> bool:
     return _POLICY["features"] == "auto"
 
 
+_VOLUME_DTYPES = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}
+HALF_DTYPES = (torch.bfloat16, torch.float16)
+
+
 def volume_dtype() -> torch.dtype:
-    return torch.bfloat16 if _POLICY["precision"] == "bf16" else torch.float32
+    return _VOLUME_DTYPES[_POLICY["precision"]]
 
 
 def conv_impl_for(cin: int, cout: int, stride: int, transposed: bool) -> int:
@@ -108,7 +115,7 @@ def _need(t: torch.Tensor, name: str, dtype=torch.float32, ndim: Optional[int] =
 
 
 def _dt(dtype: torch.dtype) -> int:
-    return BF16 if dtype == torch.bfloat16 else F32
+    return BF16 if dtype == torch.bfloat16 else (F16 if dtype == torch.float16 else F32)
 
 
 @dataclass
@@ -296,11 +303,14 @@ def conv_desc(b, cin, cout, din, hin, win, stride, transposed, relu, in_dtype, o
                     impl=impl)
 
 
-def conv3d_pack_weight(weight: torch.Tensor, cin: int, cout: int, transposed: bool, impl: int, stride: int = 1) -> torch.Tensor:
+def conv3d_pack_weight(weight: torch.Tensor, cin: int, cout: int, transposed: bool, impl: int, stride: int = 1,
+                       dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
     """PyTorch-layout fp32 conv weight -> the packed buffer `impl` consumes (uint8 tensor).
-    The tcgen05 buffer embeds the layer's MMA program, which depends on stride / transposed."""
+    The tcgen05 buffer embeds the layer's MMA program, which depends on stride / transposed, and holds the weights in the
+    2-byte type of the volumes the layer will run on (`dtype`: bf16 or fp16; the direct kernel's weights are fp32)."""
     _need(weight, "weight", torch.float32, 5)
-    desc = conv_desc(1, cin, cout, 1, 1, 1, stride, transposed, 0, torch.float32, torch.float32, cout == 1, impl)
+    wdt = dtype if (impl == CONV_TCGEN05 and dtype in HALF_DTYPES) else (torch.bfloat16 if impl == CONV_TCGEN05 else torch.float32)
+    desc = conv_desc(1, cin, cout, 1, 1, 1, stride, transposed, 0, wdt, wdt, cout == 1, impl)
     lib = _lib.load()
     nbytes = lib.damvs_conv3d_packed_weight_bytes(ctypes.byref(desc))
     if nbytes == 0:

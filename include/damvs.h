@@ -39,7 +39,10 @@ enum damvs_status {
   DAMVS_ERR_NO_DEVICE = 4    /* device is not sm_100 */
 };
 
-enum damvs_dtype { DAMVS_F32 = 0, DAMVS_BF16 = 1 };
+/* Element types of cost volumes / CostRegNet activations.  DAMVS_F16 (IEEE half: 11 significand bits, 8x finer than
+ * bf16 at the same width and the same tensor-core rate) is the inference pipeline's reduced-precision format; values
+ * saturate to +-65504 on store.  DAMVS_BF16 stays the training format (gradients need the exponent range). */
+enum damvs_dtype { DAMVS_F32 = 0, DAMVS_BF16 = 1, DAMVS_F16 = 2 };
 enum damvs_agg_mode { DAMVS_AGG_VARIANCE = 0, DAMVS_AGG_ADAPTIVE = 1 };
 enum damvs_conv_impl { DAMVS_CONV_DIRECT = 0, DAMVS_CONV_TCGEN05 = 1 };
 

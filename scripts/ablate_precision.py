@@ -15,7 +15,10 @@ Rows (what is rounded):
   B  feat_fp16           fp16 features (fp32 blend/accumulate), fp32 cost volume, fp32 direct convolutions
   C  conv_bf16           fp32 features, bf16 cost volume, tcgen05 convolutions with bf16 weights/activations  (north star's
                          "bf16 on the tensor-core convs")
-  D  benchmarked         fp16 features, bf16 cost volume, tcgen05 convolutions  (bench.py --precision bf16)
+  D  bf16 pipeline       fp16 features, bf16 cost volume, tcgen05 convolutions  (precision "bf16": round 1's benchmarked mode)
+  E  vol_fp16            fp32 features, cost volume rounded to fp16, fp32 direct convolutions
+  F  conv_fp16           fp32 features, fp16 cost volume, tcgen05 convolutions with fp16 weights/activations
+  G  fp16 pipeline       fp16 features, fp16 cost volume, tcgen05 convolutions  (precision "fp16": bench.py's default)
 
 Usage (GPU box):  python scripts/ablate_precision.py [--out gpurun_out/ablation.json] [--small]
 """
@@ -41,16 +44,17 @@ def nets():
 
 
 @torch.no_grad()
-def run_stage(dm, runner, s, feats, proj, dv, feat_half: bool, vol_dtype, conv_bf16: bool):
+def run_stage(dm, runner, s, feats, proj, dv, feat_half: bool, vol_dtype, conv_half):
     from damvsnet_b200 import ops
     net, cr = runner.depthnet, runner.cost_regularization[s]
     rot_trans = net.stage_rot_trans(proj)
     nhwc = ops.features_to_nhwc_half_multi(feats) if feat_half else [ops.features_to_nhwc(f) for f in feats]
     wn = net.weight_net[s].folded()
     vol = ops.warp_aggregate(nhwc[0], nhwc[1:], rot_trans, dv, wn, "adaptive", vol_dtype)
-    if conv_bf16:
-        with dm.precision("bf16"):
-            logits = cr.forward_g8(vol if vol.dtype == torch.bfloat16 else ops.G8Volume(vol.data.bfloat16()))
+    if conv_half:       # "bf16" | "fp16": tcgen05 convolutions on volumes / weights of that type
+        hd = torch.bfloat16 if conv_half == "bf16" else torch.float16
+        with dm.precision(conv_half):
+            logits = cr.forward_g8(vol if vol.dtype == hd else ops.G8Volume(vol.data.to(hd)))
     else:
         with dm.precision("fp32"):
             logits = cr.forward_g8(vol if vol.dtype == torch.float32 else ops.G8Volume(vol.data.float()))
@@ -58,10 +62,13 @@ def run_stage(dm, runner, s, feats, proj, dv, feat_half: bool, vol_dtype, conv_b
     return {"depth": depth, "photometric_confidence": conf, "variance": var, "prob_volume": prob}
 
 
-ROWS = (("A vol_bf16", False, torch.bfloat16, False),
-        ("B feat_fp16", True, torch.float32, False),
-        ("C conv_bf16", False, torch.bfloat16, True),
-        ("D benchmarked", True, torch.bfloat16, True))
+ROWS = (("A vol_bf16", False, torch.bfloat16, None),
+        ("B feat_fp16", True, torch.float32, None),
+        ("C conv_bf16", False, torch.bfloat16, "bf16"),
+        ("D bf16 pipeline", True, torch.bfloat16, "bf16"),
+        ("E vol_fp16", False, torch.float16, None),
+        ("F conv_fp16", False, torch.float16, "fp16"),
+        ("G fp16 pipeline", True, torch.float16, "fp16"))
 
 
 def main():

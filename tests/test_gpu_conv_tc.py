@@ -1,7 +1,7 @@
-"""tcgen05 implicit-GEMM conv blocks against torch fp32 convolutions on bf16-representable data.
+"""tcgen05 implicit-GEMM conv blocks against torch fp32 convolutions on bf16- / fp16-representable data.
 
-Inputs and weights are rounded to bf16 first, so the only differences left are the fp32
-accumulation order and the final bf16 rounding of the output (relative 2^-8)."""
+Inputs and weights are rounded to the volumes' 2-byte type first, so the only differences left are the fp32
+accumulation order and the final rounding of the output (relative 2^-8 for bf16, 2^-11 for fp16)."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -13,8 +13,11 @@ def dev():
     return torch.device("cuda:0")
 
 
-def _bf(t):
-    return t.bfloat16().float()
+HALF = {"bf16": torch.bfloat16, "fp16": torch.float16}
+
+
+def _bf(t, dt=torch.bfloat16):
+    return t.to(dt).float()
 
 
 CASES = [
@@ -36,40 +39,43 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
 @pytest.mark.parametrize("cin,cout,stride,transposed,ext", CASES)
-def test_tc_conv_block_matches_torch(cin, cout, stride, transposed, ext):
+def test_tc_conv_block_matches_torch(cin, cout, stride, transposed, ext, prec):
     import damvsnet_b200 as dm
+    hd = HALF[prec]
     g = torch.Generator().manual_seed(cin * 1000 + cout * 10 + stride + (5 if transposed else 0))
     if transposed:
         blk = dm.Deconv3d(cin, cout, stride=2, padding=1, output_padding=1)
     else:
         blk = dm.Conv3d(cin, cout, stride=stride, padding=1)
     with torch.no_grad():
-        blk.conv.weight.copy_(_bf(blk.conv.weight))
+        blk.conv.weight.copy_(_bf(blk.conv.weight, hd))
         blk.bn.weight.copy_(0.8 + 0.4 * torch.rand(cout, generator=g))
         blk.bn.bias.copy_(0.1 * torch.randn(cout, generator=g))
         blk.bn.running_mean.copy_(0.05 * torch.randn(cout, generator=g))
         blk.bn.running_var.copy_(0.5 + torch.rand(cout, generator=g))
     blk = blk.eval()
     B = 2
-    x = _bf(torch.randn(B, cin, *ext, generator=g))
+    x = _bf(torch.randn(B, cin, *ext, generator=g), hd)
     with torch.no_grad():
         want = torch.relu(blk.bn(blk.conv(x)))
-    skip = _bf(torch.randn(want.shape, generator=g))
+    skip = _bf(torch.randn(want.shape, generator=g), hd)
     blk = blk.to(dev())
-    with dm.precision("bf16", "tcgen05"):
-        vol = dm.G8Volume.from_ncdhw(x.to(dev()), torch.bfloat16)
+    with dm.precision(prec, "tcgen05"):
+        vol = dm.G8Volume.from_ncdhw(x.to(dev()), hd)
         got = blk.forward_g8(vol).to_ncdhw().cpu()
-        sk = dm.G8Volume.from_ncdhw(skip.to(dev()), torch.bfloat16)
+        sk = dm.G8Volume.from_ncdhw(skip.to(dev()), hd)
         got_skip = blk.forward_g8(vol, skip=sk).to_ncdhw().cpu()
     torch.cuda.synchronize()
     assert got.shape == want.shape
-    tol = 2 ** -7
+    tol = 2 ** -7 if prec == "bf16" else 2 ** -10
     err = (got - want).abs()
-    assert (err <= tol * want.abs() + 2e-3).all(), (err.max().item(), (err / want.abs().clamp_min(1e-2)).max().item())
+    floor = 2e-3 if prec == "bf16" else 3e-4     # fp32 accumulation-order noise on O(1) sums of up to 1728 products
+    assert (err <= tol * want.abs() + floor).all(), (err.max().item(), (err / want.abs().clamp_min(1e-2)).max().item())
     ws = want + skip
     err = (got_skip - ws).abs()
-    assert (err <= tol * ws.abs() + tol * want.abs() + 4e-3).all(), err.max().item()
+    assert (err <= tol * ws.abs() + tol * want.abs() + 2 * floor).all(), err.max().item()
 
 
 @pytest.mark.parametrize("shape", [
@@ -81,23 +87,42 @@ def test_tc_conv_block_matches_torch(cin, cout, stride, transposed, ext):
     (1, 5, 120, 600),     # more tiles than resident CTAs, odd depth: ring position carried across tiles
     (2, 8, 126, 330),
 ])
-def test_tc_prob_conv_plain_output(shape):
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+def test_tc_prob_conv_plain_output(shape, prec):
     import damvsnet_b200 as dm
     from damvsnet_b200 import ops
+    hd = HALF[prec]
     g = torch.Generator().manual_seed(9)
-    w = _bf(torch.randn(1, 8, 3, 3, 3, generator=g) * 0.2)
-    x = _bf(torch.randn(shape[0], 8, *shape[1:], generator=g))
+    w = _bf(torch.randn(1, 8, 3, 3, 3, generator=g) * 0.2, hd)
+    x = _bf(torch.randn(shape[0], 8, *shape[1:], generator=g), hd)
     want = F.conv3d(x, w, None, padding=1).squeeze(1)
-    packed = ops.conv3d_pack_weight(w.to(dev()), 8, 1, False, ops.CONV_TCGEN05)
-    vol = dm.G8Volume.from_ncdhw(x.to(dev()), torch.bfloat16)
+    packed = ops.conv3d_pack_weight(w.to(dev()), 8, 1, False, ops.CONV_TCGEN05, 1, hd)
+    vol = dm.G8Volume.from_ncdhw(x.to(dev()), hd)
     got = ops.conv3d(vol, packed, None, None, 1, 1, False, False, None, torch.float32, True, ops.CONV_TCGEN05).cpu()
     assert got.shape == want.shape
     assert (got - want).abs().max() < 1e-4 * max(1.0, want.abs().max().item())
 
 
+def test_packed_weights_of_the_other_half_type_are_rejected():
+    """A blob packed for bf16 volumes must not be silently consumed as fp16 (same width, different bits)."""
+    import damvsnet_b200 as dm
+    from damvsnet_b200 import ops
+    cr = dm.CostRegNet(8, 8).eval().to(dev())
+    x = torch.rand(1, 8, 8, 16, 24, device=dev())
+    with torch.no_grad():
+        with dm.precision("bf16"):
+            a = cr(x)
+        with dm.precision("fp16"):
+            b = cr(x)                       # re-packs: the cache is keyed on the volume type
+    assert torch.isfinite(a).all() and torch.isfinite(b).all()
+    assert (a - b).abs().max() < 0.05 * max(1.0, a.abs().max().item())
+    assert len({k[-1] for k in cr.conv0._packed}) == 2
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
 @pytest.mark.parametrize("stage", [0, 1, 2])
-def test_cost_reg_net_tc_vs_direct_bf16(stage):
-    """Whole U-Net: tcgen05 path against the direct fp32-accumulate kernels on the same bf16 storage."""
+def test_cost_reg_net_tc_vs_direct_bf16(stage, prec):
+    """Whole U-Net: tcgen05 path against the direct fp32-accumulate kernels on the same 2-byte storage."""
     import damvsnet_b200 as dm
     from damvsnet_b200 import synthetic
     sd = synthetic.hot_path_state_dict(seed=2)
@@ -107,10 +132,11 @@ def test_cost_reg_net_tc_vs_direct_bf16(stage):
     cr.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, strict=True)
     cr = cr.to(dev())
     x = (torch.rand(1, cin, 8, 24, 40) * 0.5).to(dev())
-    with dm.precision("bf16", "direct"):
+    with dm.precision(prec, "direct"):
         a = cr(x).cpu()
-    with dm.precision("bf16", "tcgen05"):
+    with dm.precision(prec, "tcgen05"):
         b = cr(x).cpu()
     scale = a.abs().max().item()
-    assert (a - b).abs().max().item() < 3e-2 * max(scale, 1.0), ((a - b).abs().max().item(), scale)
-    assert (a - b).abs().mean().item() < 3e-3 * max(scale, 1.0)
+    k = 1.0 if prec == "bf16" else 0.125
+    assert (a - b).abs().max().item() < 3e-2 * k * max(scale, 1.0), ((a - b).abs().max().item(), scale)
+    assert (a - b).abs().mean().item() < 3e-3 * k * max(scale, 1.0)
