@@ -172,6 +172,19 @@ def cpu_step_fn(args, height, width):
     nd = [int(x) for x in args.ndepths.split(",")]
     sd = synthetic.hot_path_state_dict(seed=0, mode=args.mode)
     stages = make_workload(height, width, args.nviews, nd, seed=0)
+    # hypotheses as the cascade produces them (the GPU arm's workload): stage 1 = the plane-sweep range, stages 2/3 =
+    # uncertainty-aware samples of smooth previous-stage maps -- here through the oracle's CPU samplers
+    from oracle import damvs_oracle as O
+    rng = synthetic.make_depth_range(1, 192)
+    for s in range(len(stages)):
+        fs, p, _ = stages[s]
+        b, _, h, w = fs[0].shape
+        if s == 0:
+            dv = O.first_stage_samples(rng, nd[s]).view(b, nd[s], 1, 1).expand(b, nd[s], h, w).contiguous()
+        else:
+            pd, pv = synthetic.make_prev_maps(s, b, height, width, seed=0)
+            dv = O.stage_hypotheses(pd, pv, nd[s], height, width, synthetic.STAGE_SCALES[s])
+        stages[s] = (fs, p, dv)
     from oracle import ref_loader
     if ref_loader.available():
         import warnings
@@ -182,8 +195,6 @@ def cpu_step_fn(args, height, width):
                 warnings.simplefilter("ignore")
                 ref_loader.hot_path_forward(depthnet, crs, stages)
         return step, "reference"
-    from oracle import damvs_oracle as O
-
     def step():
         with torch.no_grad():
             for s, (f, p, d) in enumerate(stages):
@@ -220,6 +231,8 @@ def cpu_leg(args, max_steps, budget_s):
 def config_of(args, extra=None):
     c = {"workload": f"DTU-test {args.height}x{args.width}, N={args.nviews}, D={args.ndepths.replace(',', '/')}, batch 1, "
                      f"agg={args.mode} (BASELINE.json configs[1])",
+         "hypotheses": "as the cascade produces them: stage 1 = plane-sweep range [425, 931] mm, stages 2/3 = uncertainty-aware "
+                       "samples (+-12 / +-3 mm) of smooth synthetic previous-stage depth / variance maps (teacher forcing)",
          "precision": args.precision,
          "l2": "no flush needed: per-step inputs (0.4 GB) and intermediates (>2 GB) exceed the 126 MB L2"}
     if extra:
@@ -526,7 +539,22 @@ def run_ours(args):
     sd = synthetic.hot_path_state_dict(seed=0, mode=args.mode)
     runner = HotPathRunner(sd, mode=args.mode, device=dev)
     host_stages = make_workload(args.height, args.width, args.nviews, nd, seed=rank)
-    dev_stages = [([f.to(dev) for f in fs], p.to(dev), d.to(dev)) for fs, p, d in host_stages]
+    # Hypotheses as the cascade produces them (reference models/cas_mvsnet.py:236-296): stage 1 sweeps the plane-sweep
+    # range, stages 2/3 are uncertainty-aware samples of the previous stage's depth / variance -- here smooth synthetic
+    # maps (teacher forcing), sampled on the device by the fused sampler.  The device-resident leg (`value`) and the
+    # host-buffer leg (`e2e`) run on exactly these hypotheses; the latter uploads the maps, not the hypotheses.
+    depth_range = synthetic.make_depth_range(1, 192)
+    prev_maps = [None] + [synthetic.make_prev_maps(s, 1, args.height, args.width, seed=rank) for s in range(1, len(nd))]
+    dev_stages = []
+    for s, (fs, p, _) in enumerate(host_stages):
+        b, _, h, w = fs[0].shape
+        if s == 0:
+            dv = runner._range_hypotheses(depth_range, nd[s], b, h, w)
+        else:
+            dv = dm.ops.stage_hypotheses(prev_maps[s][0].to(dev), prev_maps[s][1].to(dev), nd[s], args.height, args.width, args.height // h)
+        dev_stages.append(([f.to(dev) for f in fs], p.to(dev), dv))
+    host_inputs = [(fs, p, prev_maps[s]) for s, (fs, p, _) in enumerate(host_stages)]
+    cascade = (depth_range.pin_memory(), nd, args.height, args.width)
 
     def barrier():
         if world > 1:
@@ -568,8 +596,8 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         fmt = "nhwc_f16" if args.precision != "fp32" else "nchw_f32"
-        pinned = runner.pin_stages(host_stages, feature_format=fmt)
-        warm = [runner.submit_host(pinned) for _ in range(3)]      # also allocates the pinned result buffers
+        pinned = runner.pin_stages(host_inputs, feature_format=fmt)
+        warm = [runner.submit_host(pinned, cascade=cascade) for _ in range(3)]      # also allocates the pinned result buffers
         for t in warm:
             runner.collect(t)
             runner.release(t)
@@ -579,7 +607,7 @@ def run_ours(args):
             # read back to pinned host memory and waited for inside the timed region
             pending = None
             for _ in range(n):
-                t = runner.submit_host(pinned)
+                t = runner.submit_host(pinned, cascade=cascade)
                 if pending is not None:
                     runner.collect(pending)
                     runner.release(pending)
@@ -589,12 +617,14 @@ def run_ours(args):
         e_steps = max(3, min(steps, 20))
         e_ms, _, e_reps = timed_batches(run_host, e_steps, args.min_seconds, barrier, dev, max_reps=20)
         e2e = {"value": world * e_steps / (e_ms / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": runner.h2d_bytes(pinned), "d2h_bytes_per_step": runner.d2h_bytes(host_stages),
+               "h2d_bytes_per_step": runner.h2d_bytes(pinned) + depth_range.numel() * 4, "d2h_bytes_per_step": runner.d2h_bytes(host_stages),
                "steps": e_steps, "repetitions": e_reps, "numa": numa,
                "api": "HotPathRunner.submit_host/collect, 2 views in flight; pinned host inputs: features "
                       + ("fp16 channels_last [B,C,h,w] (the layout and width the gather kernel consumes; zero-copy on the device)"
                          if fmt == "nhwc_f16" else "fp32 NCHW")
-                      + ", projection matrices, fp32 hypotheses; depth, confidence, variance of 3 stages out to pinned host memory"}
+                      + ", projection matrices, the plane-sweep range (stage 1) and the previous stage's depth / variance maps (stages 2, 3: "
+                        "hypotheses are sampled on the device by the fused sampler, as in the cascade); depth, confidence, variance of 3 "
+                        "stages out to pinned host memory"}
         del pinned
 
     # ---- roofline: per-call device times of the hot kernels, measured live with CUDA events (eager pass, one view)

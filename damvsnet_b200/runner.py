@@ -125,15 +125,24 @@ class HotPathRunner:
             if feature_format == "nhwc_f16":
                 f = f.clamp(-65504.0, 65504.0).to(torch.float16).contiguous(memory_format=torch.channels_last)
             return f.pin_memory()
-        return [([feat(f) for f in feats], proj.pin_memory(), None if dv is None else dv.pin_memory()) for feats, proj, dv in stages]
+
+        def pin(t):
+            if t is None:
+                return None
+            if isinstance(t, (tuple, list)):
+                return tuple(pin(x) for x in t)
+            return t.pin_memory()
+        return [([feat(f) for f in feats], proj.pin_memory(), pin(dv)) for feats, proj, dv in stages]
 
     @staticmethod
     def h2d_bytes(stages: Sequence[StageInput]) -> int:
-        n = 0
-        for feats, proj, dv in stages:
-            n += sum(f.numel() * f.element_size() for f in feats) + proj.numel() * proj.element_size() + \
-                (0 if dv is None else dv.numel() * dv.element_size())
-        return n
+        def nb(t):
+            if t is None:
+                return 0
+            if isinstance(t, (tuple, list)):
+                return sum(nb(x) for x in t)
+            return t.numel() * t.element_size()
+        return sum(nb(feats) + nb(proj) + nb(dv) for feats, proj, dv in stages)
 
     @staticmethod
     def d2h_bytes(stages: Sequence[StageInput]) -> int:
@@ -149,7 +158,9 @@ class HotPathRunner:
         `cascade` = (depth_range [B,Dtot] host tensor, ndepths, height, width) chains the stages as
         CascadeMVSNet.forward does (reference models/cas_mvsnet.py:236-296): a stage whose hypotheses are `None`
         gets them on the device -- stage 1 from the plane-sweep range, later stages from the previous stage's depth
-        and variance through the fused sampling kernel -- so only features and cameras cross PCIe."""
+        and variance through the fused sampling kernel -- so only features and cameras cross PCIe.  A stage may also
+        carry a `(prev_depth, prev_variance)` pair of [B,hp,wp] host maps in place of its hypotheses (teacher-forced
+        cascade): they are uploaded (h*w*8 bytes instead of D*h*w*4) and sampled on the device by the same kernel."""
         dev = self.device
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=dev)
@@ -164,24 +175,41 @@ class HotPathRunner:
         # set k is overwritten only after the kernels that last read it have finished
         bset = self._submits % 2
         self._submits += 1
-        shp = lambda t: None if t is None else (tuple(t.shape), t.dtype, tuple(t.stride()))
+        def shp(t):
+            if t is None:
+                return None
+            if isinstance(t, (tuple, list)):
+                return tuple(shp(x) for x in t)
+            return (tuple(t.shape), t.dtype, tuple(t.stride()))
+
+        def dev_like(t):
+            # empty_like keeps the strides (channels_last features stay channels_last: one flat memcpy each)
+            if t is None:
+                return None
+            if isinstance(t, (tuple, list)):
+                return tuple(dev_like(x) for x in t)
+            return torch.empty_like(t, device=dev)
+
+        def upload(src, dst):
+            if src is None:
+                return
+            if isinstance(src, (tuple, list)):
+                for a, b2 in zip(src, dst):
+                    upload(a, b2)
+                return
+            dst.copy_(src, non_blocking=True)
         if self._dev_in[bset] is None or [[shp(t) for t in st[0]] + [shp(st[1]), shp(st[2])] for st in self._dev_in[bset]] != \
                 [[shp(f) for f in feats] + [shp(proj), shp(dv)] for feats, proj, dv in stages]:
-            # empty_like keeps the strides (channels_last features stay channels_last: one flat memcpy each)
-            self._dev_in[bset] = [([torch.empty_like(f, device=dev) for f in feats],
-                                torch.empty(proj.shape, dtype=proj.dtype, device=dev),
-                                None if dv is None else torch.empty(dv.shape, dtype=dv.dtype, device=dev)) for feats, proj, dv in stages]
+            self._dev_in[bset] = [([dev_like(f) for f in feats], dev_like(proj), dev_like(dv)) for feats, proj, dv in stages]
             self._set_done[bset] = None
         if self._set_done[bset] is not None:
             copy.wait_event(self._set_done[bset])
         uploaded, ready = [], []
         with torch.cuda.stream(copy):
             for (feats, proj, dv), (bfe, bpr, bdv) in zip(stages, self._dev_in[bset]):
-                for src, dst in zip(feats, bfe):
-                    dst.copy_(src, non_blocking=True)
-                bpr.copy_(proj, non_blocking=True)
-                if dv is not None:
-                    bdv.copy_(dv, non_blocking=True)
+                upload(feats, bfe)
+                upload(proj, bpr)
+                upload(dv, bdv)
                 ev = torch.cuda.Event()
                 ev.record(copy)
                 uploaded.append((bfe, bpr, bdv))
@@ -198,16 +226,14 @@ class HotPathRunner:
         prev = None
         for i, ((dfe, dpr, ddv), ev) in enumerate(zip(uploaded, ready)):
             compute.wait_event(ev)
-            if ddv is None:
+            if ddv is None or isinstance(ddv, tuple):
                 from . import ops
                 rng_host, ndepths, height, width = cascade
                 b, _, h, w = dfe[0].shape
-                if prev is None:          # plane-sweep range -> evenly spaced hypotheses (models/module.py:1003-1010)
-                    rng = rng_host.to(dev, non_blocking=True)
-                    lo, hi = rng[:, 0], rng[:, -1]
-                    vals = lo.unsqueeze(1) + torch.arange(ndepths[i], device=dev, dtype=torch.float32).view(1, -1) * \
-                        ((hi - lo) / (ndepths[i] - 1)).unsqueeze(1)
-                    ddv = vals.view(b, -1, 1, 1).expand(b, ndepths[i], h, w).contiguous()
+                if isinstance(ddv, tuple):   # teacher-forced cascade: the previous stage's (depth, variance) maps were handed in
+                    ddv = ops.stage_hypotheses(ddv[0], ddv[1], ndepths[i], height, width, height // h)
+                elif prev is None:          # plane-sweep range -> evenly spaced hypotheses (models/module.py:1003-1010)
+                    ddv = self._range_hypotheses(rng_host, ndepths[i], b, h, w)
                 else:
                     ddv = ops.stage_hypotheses(prev["depth"], prev["variance"], ndepths[i], height, width, height // h)
             out = self.run_stage(i, dfe, dpr, ddv)
@@ -225,6 +251,13 @@ class HotPathRunner:
         fin = torch.cuda.Event()
         fin.record(d2h)
         return HostTicket(host, fin)
+
+    def _range_hypotheses(self, depth_range: torch.Tensor, ndepth: int, b: int, h: int, w: int) -> torch.Tensor:
+        """First-stage hypotheses [B,D,h,w] from the plane-sweep range [B,Dtot] (reference models/module.py:1003-1010)."""
+        rng = depth_range.to(self.device, non_blocking=True)
+        lo, hi = rng[:, 0], rng[:, -1]
+        vals = lo.unsqueeze(1) + torch.arange(ndepth, device=self.device, dtype=torch.float32).view(1, -1) * ((hi - lo) / (ndepth - 1)).unsqueeze(1)
+        return vals.view(b, -1, 1, 1).expand(b, ndepth, h, w).contiguous()
 
     def collect(self, ticket: "HostTicket") -> List[Dict[str, torch.Tensor]]:
         """Wait for a submitted view; the returned pinned host tensors are recycled by a later submit_host

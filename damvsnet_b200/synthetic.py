@@ -123,6 +123,22 @@ def make_stage_inputs(stage_idx: int, batch: int, nviews: int, height: int, widt
     return feats, projs[f"stage{stage_idx + 1}"], dv.contiguous()
 
 
+def make_prev_maps(stage_idx: int, batch: int, height: int, width: int, seed: int = 0) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Smooth synthetic (depth, variance) maps [B,hp,wp] of the stage BEFORE `stage_idx` (1 or 2), at that stage's
+    resolution: what CascadeMVSNet.forward feeds to uncertainty_aware_samples (reference models/cas_mvsnet.py:236-274).
+    The surface and the half-ranges (12 mm / 3 mm) are those of make_stage_inputs, so the sampled hypotheses sweep the
+    same band; `seed` shifts the phase so ranks / views differ."""
+    assert stage_idx in (1, 2)
+    sp = STAGE_SCALES[stage_idx - 1]
+    hp, wp = height // sp, width // sp
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, hp), torch.linspace(0, 1, wp), indexing="ij")
+    ph = 0.37 * seed
+    surf = 600.0 + 120.0 * torch.sin(3.0 * xx + 0.5 + ph) * torch.cos(2.0 * yy + 0.5 * ph)
+    half = 12.0 if stage_idx == 1 else 3.0
+    var = half * (1.0 + 0.1 * torch.sin(5.0 * xx + ph) * torch.cos(4.0 * yy))
+    return (surf.unsqueeze(0).repeat(batch, 1, 1).contiguous(), var.unsqueeze(0).repeat(batch, 1, 1).contiguous())
+
+
 def hot_path_state_dict(in_channels=STAGE_CHANNELS, base_channels=(8, 8, 8), seed: int = 0,
                         mode: str = "adaptive") -> Dict[str, torch.Tensor]:
     """Random, *non-degenerate* parameters for the hot path under the reference's

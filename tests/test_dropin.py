@@ -95,7 +95,7 @@ def test_uncertainty_samples_keep_the_undetach_gradient_path():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("prec", ["fp32", "fp16", "bf16"])
 def test_reference_cascade_forward_runs_on_the_native_hot_path(prec):
     """The reference's CascadeMVSNet.forward (models/cas_mvsnet.py:190-319), images in -> output dict, executed on the
     GPU twice: as is (PyTorch ops, strict fp32), and with dropin.install() (its FPN / GeoFeatureFusion, this package's
@@ -141,7 +141,7 @@ def test_reference_cascade_forward_runs_on_the_native_hot_path(prec):
         finally:
             dropin.uninstall()
             dm.set_precision("fp32")
-        assert _lib.launch_count() - n0 >= 3 * 13, "the native kernels did not run"
+        assert _lib.launch_count() - n0 >= 3 * 14, "the native kernels did not run"
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
     assert set(got) == set(want) == {"stage1", "stage2", "stage3", "depth", "photometric_confidence", "variance", "prob_volume",

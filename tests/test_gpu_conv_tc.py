@@ -62,11 +62,16 @@ def test_tc_conv_block_matches_torch(cin, cout, stride, transposed, ext, prec):
         want = torch.relu(blk.bn(blk.conv(x)))
     skip = _bf(torch.randn(want.shape, generator=g), hd)
     blk = blk.to(dev())
-    with dm.precision(prec, "tcgen05"):
+    with dm.precision(prec, "tcgen05"), torch.no_grad():      # inference: BatchNorm / ReLU / skip fused into the conv epilogue
         vol = dm.G8Volume.from_ncdhw(x.to(dev()), hd)
         got = blk.forward_g8(vol).to_ncdhw().cpu()
         sk = dm.G8Volume.from_ncdhw(skip.to(dev()), hd)
         got_skip = blk.forward_g8(vol, skip=sk).to_ncdhw().cpu()
+    if prec == "bf16":
+        # with gradients enabled the same block runs as raw conv -> BatchNorm/ReLU/skip kernels (autograd.ConvBlockFn)
+        with dm.precision(prec, "tcgen05"):
+            got_tape = blk.forward_g8(vol, skip=sk).to_ncdhw().detach().cpu()
+        assert (got_tape - got_skip).abs().max() <= 2 ** -6 * got_skip.abs().max() + 1e-2
     torch.cuda.synchronize()
     assert got.shape == want.shape
     tol = 2 ** -7 if prec == "bf16" else 2 ** -10
@@ -132,9 +137,9 @@ def test_cost_reg_net_tc_vs_direct_bf16(stage, prec):
     cr.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, strict=True)
     cr = cr.to(dev())
     x = (torch.rand(1, cin, 8, 24, 40) * 0.5).to(dev())
-    with dm.precision(prec, "direct"):
+    with dm.precision(prec, "direct"), torch.no_grad():
         a = cr(x).cpu()
-    with dm.precision(prec, "tcgen05"):
+    with dm.precision(prec, "tcgen05"), torch.no_grad():
         b = cr(x).cpu()
     scale = a.abs().max().item()
     k = 1.0 if prec == "bf16" else 0.125

@@ -480,7 +480,7 @@ def test_runner_host_pipeline_fp16_channels_last_features(dm):
                 for k in ("depth", "photometric_confidence", "variance"):
                     assert torch.equal(a[k].cpu(), b[k]), k
             runner.release(t)
-        assert launches == 3 * 13, launches          # warp + 11 convs + head per stage: no repack launch
+        assert launches == 3 * 14, launches          # warp + 12 conv launches (conv6 = 2) + head per stage: no repack launch
         with pytest.raises(ValueError):
             runner.pin_stages(host, feature_format="nhwc_bf16")
 
@@ -556,6 +556,37 @@ def test_host_cascade_pipeline_matches_device_cascade(dm):
             for k in ("depth", "photometric_confidence", "variance"):
                 torch.testing.assert_close(got[s][k], want[f"stage{s + 1}"][k].cpu(), rtol=1e-5, atol=1e-4)
         runner.release(t)
+
+
+def test_host_pipeline_teacher_forced_cascade_uploads_maps_not_hypotheses(dm):
+    """submit_host with a (prev_depth, prev_variance) pair in place of a stage's hypotheses: the maps are uploaded and
+    sampled on the device by the fused sampler; the result equals run_device on hypotheses sampled the same way."""
+    from damvsnet_b200 import ops, synthetic
+    from damvsnet_b200.runner import HotPathRunner
+    H, W, N, nds = 64, 96, 3, [16, 8, 8]
+    sd = synthetic.hot_path_state_dict(seed=3)
+    runner = HotPathRunner(sd, device=dev())
+    host = [synthetic.make_stage_inputs(s, 1, N, H, W, nds[s], seed=6) for s in range(3)]
+    rng = synthetic.make_depth_range(1, 192)
+    prev = [None, synthetic.make_prev_maps(1, 1, H, W, seed=1), synthetic.make_prev_maps(2, 1, H, W, seed=1)]
+    dev_stages = []
+    for s, (fs, p, _) in enumerate(host):
+        b, _, h, w = fs[0].shape
+        dv = runner._range_hypotheses(rng, nds[s], b, h, w) if s == 0 else \
+            ops.stage_hypotheses(prev[s][0].to(dev()), prev[s][1].to(dev()), nds[s], H, W, H // h)
+        dev_stages.append(([f.to(dev()) for f in fs], p.to(dev()), dv))
+    for prec, fmt in (("fp32", "nchw_f32"), ("fp16", "nhwc_f16")):
+        with dm.precision(prec):
+            want = runner.run_device(dev_stages)
+            pinned = runner.pin_stages([(fs, p, prev[s]) for s, (fs, p, _) in enumerate(host)], feature_format=fmt)
+            assert runner.h2d_bytes(pinned) < runner.h2d_bytes(runner.pin_stages(host, feature_format=fmt))
+            for _ in range(2):
+                t = runner.submit_host(pinned, cascade=(rng.pin_memory(), nds, H, W))
+                got = runner.collect(t)
+                for s in range(3):
+                    for k in ("depth", "photometric_confidence", "variance"):
+                        assert torch.equal(got[s][k], want[s][k].cpu()), (prec, s, k)
+                runner.release(t)
 
 
 @pytest.mark.parametrize("mode", ["adaptive", "variance"])
