@@ -21,10 +21,18 @@ __all__ = ["DepthNet"]
 class DepthNet(nn.Module):
     """Per-stage cost-volume pipeline (reference models/cas_mvsnet.py:10-134)."""
 
-    def __init__(self, mode="adaptive", in_channels=None):
+    def __init__(self, mode="adaptive", in_channels=None, groups=None):
+        """mode "variance" / "adaptive" are the reference's (models/cas_mvsnet.py:11-16).  mode "groupwise" with
+        `groups` = per-stage group counts is NOT in the reference: the group-wise correlation cost volume BASELINE.json's
+        north star names (inference only; CostRegNet(in_channels=max(groups, 8)) consumes it)."""
         super().__init__()
         self.mode = mode
-        assert mode in ("variance", "adaptive"), "Don't support {}!".format(mode)
+        assert mode in ("variance", "adaptive", "groupwise"), "Don't support {}!".format(mode)
+        self.groups = None
+        if mode == "groupwise":
+            if groups is None:
+                raise ValueError('mode "groupwise" needs groups=[G per stage]')
+            self.groups = [int(g) for g in (groups if isinstance(groups, (list, tuple)) else [groups])]
         if self.mode == "adaptive":
             self.weight_net = nn.ModuleList([AggWeightNetVolume(in_channels[i]) for i in range(len(in_channels))])
 
@@ -42,6 +50,13 @@ class DepthNet(nn.Module):
         """Aggregated cost volume (reference models/cas_mvsnet.py:30-87) as a G8 volume."""
         rot_trans = self.stage_rot_trans(proj_matrices)
         out_dtype = out_dtype or ops.volume_dtype()
+        if self.mode == "groupwise":
+            if ag.wants_grad(*features):
+                raise NotImplementedError("group-wise correlation is an inference-only variant (no backward kernel)")
+            half = out_dtype in ops.HALF_DTYPES and ops.half_features()
+            nhwc = ops.features_to_nhwc_half_multi(features) if half else [ops.features_to_nhwc(f) for f in features]
+            g = self.groups[min(stage_idx, len(self.groups) - 1)]
+            return ops.warp_groupwise(nhwc[0], nhwc[1:], rot_trans, depth_values, g, out_dtype)
         wn = self.weight_net[stage_idx] if self.mode == "adaptive" else None
         batch_stats = wn is not None and wn.training
         params = tuple(wn.w_net.parameters()) if wn is not None else ()

@@ -297,6 +297,35 @@ def warp_aggregate(ref_nhwc: torch.Tensor, src_nhwc: Sequence[torch.Tensor], rot
     return out
 
 
+def warp_groupwise(ref_nhwc: torch.Tensor, src_nhwc: Sequence[torch.Tensor], rot_trans: torch.Tensor,
+                   depth_values: torch.Tensor, groups: int, out_dtype: torch.dtype) -> G8Volume:
+    """Fused warp + group-wise correlation (NOT in the reference; BASELINE.json configs[4]) -> G8 volume of
+    max(groups, 8) channels: cost[g] = mean_v mean_{c in g} ref[c] * warp_v[c] (csrc/warp_gwc.cu)."""
+    fdt = ref_nhwc.dtype if isinstance(ref_nhwc, torch.Tensor) else None
+    if fdt not in (torch.float32, torch.float16):
+        raise ValueError("features must be fp32 or fp16 NHWC tensors")
+    _need(ref_nhwc, "ref_nhwc", fdt, 4)
+    b, h, w, c = ref_nhwc.shape
+    if c not in (8, 16, 32) or groups not in (4, 8, 16, 32) or groups > c:
+        raise ValueError(f"group-wise correlation needs C in (8,16,32), groups in (4,8,16,32) and groups <= C; got C={c}, groups={groups}")
+    n_src = len(src_nhwc)
+    for i, s in enumerate(src_nhwc):
+        _need(s, f"src_nhwc[{i}]", fdt, 4)
+        if s.shape != ref_nhwc.shape or not s.is_contiguous():
+            raise ValueError("source features must be contiguous and shaped like the reference feature")
+    _need(rot_trans, "rot_trans", torch.float32, 3)
+    if tuple(rot_trans.shape) != (n_src, b, 12):
+        raise ValueError(f"rot_trans must be [{n_src},{b},12], got {tuple(rot_trans.shape)}")
+    dv, per_pixel, d = _hyp_flags(depth_values, b, h, w)
+    out = G8Volume.empty(b, max(groups, 8), d, h, w, out_dtype, ref_nhwc.device)
+    ptrs = (ctypes.c_void_p * n_src)(*[s.data_ptr() for s in src_nhwc])
+    nbytes = (n_src + 1) * b * c * h * w * ref_nhwc.element_size() + dv.numel() * 4 + out.data.numel() * out.data.element_size()
+    with torch.cuda.device_of(ref_nhwc), _timed("warp_gwc", bytes=float(nbytes)):
+        _lib.check(_lib.load().damvs_warp_gwc_fwd(_p(ref_nhwc.contiguous()), ptrs, n_src, _p(rot_trans.contiguous()), _p(dv), _p(out.data),
+                                                  b, c, groups, d, h, w, per_pixel, _dt(fdt), _dt(out_dtype), _stream()))
+    return out
+
+
 def conv_desc(b, cin, cout, din, hin, win, stride, transposed, relu, in_dtype, out_dtype, plain_out, impl) -> ConvDesc:
     return ConvDesc(B=b, Cin=cin, Cout=cout, Din=din, Hin=hin, Win=win, stride=stride, transposed=int(transposed),
                     relu=int(relu), in_dtype=_dt(in_dtype), out_dtype=_dt(out_dtype), plain_out=int(plain_out),

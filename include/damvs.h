@@ -131,6 +131,17 @@ int damvs_warp_agg_fwd_f16(const void* ref_nhwc, const void* const* src_nhwc, in
                            const float* depth_hyp, const float* wnet, void* out_vol, int B, int C, int D, int H,
                            int W, int mode, int per_pixel_hyp, int out_dtype, void* stream);
 
+/* ---- group-wise correlation aggregation (NOT in the reference) ----------------
+ * The third aggregation mode BASELINE.json's north star names (configs[4], "groups 4-32"); the reference has only
+ * variance / adaptive (models/cas_mvsnet.py:14, 34-39).  cost[g] = mean over source views of the mean over the C/G
+ * channels of group g of ref * warp, with the reference's homography warp (models/module.py:297-332).
+ *   ref_nhwc, src_nhwc[v]  NHWC features, fp32 or fp16 (feat_dtype = DAMVS_F32 | DAMVS_F16)
+ *   out_vol                G8 volume of max(G, 8) channels (G = 4: channels 4..7 are written as zero), out_dtype any
+ *   C in {8,16,32}, G in {4,8,16,32}, G <= C.  Other arguments as damvs_warp_agg_fwd.                              */
+int damvs_warp_gwc_fwd(const void* ref_nhwc, const void* const* src_nhwc, int n_src, const float* rot_trans,
+                       const float* depth_hyp, void* out_vol, int B, int C, int G, int D, int H, int W,
+                       int per_pixel_hyp, int feat_dtype, int out_dtype, void* stream);
+
 /* ---- softmax / regression head -------------------------------------------- */
 /* Replaces models/cas_mvsnet.py:105-124 + depth_regression (models/module.py:609):
  * softmax over D, expected depth, photometric confidence (sum of p over

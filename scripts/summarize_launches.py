@@ -11,7 +11,7 @@ import re
 import sys
 from collections import OrderedDict, defaultdict
 
-CLASSES = (("nchw_to_nhwc", "repack"), ("warp_agg", "warp_agg"), ("conv3d_tc", "conv3d_tc"), ("head_", "head"), ("uncertainty", "hypotheses"))
+CLASSES = (("nchw_to_nhwc", "repack"), ("warp_agg", "warp_agg"), ("conv3d_t", "conv"), ("head_", "head"), ("uncertainty", "hypotheses"))
 
 
 def klass(name):
