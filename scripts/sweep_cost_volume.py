@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Cost-volume microbenchmark sweep (BASELINE.json configs[4]): D in {48, 96, 192}, C in {8, 16, 32}, resolutions up
 to 2048x2560, N = 5 views; device time and roofline fraction of each hot-path kernel in isolation (CUDA events around
-graph-captured launches, inputs resident).  The reference has no group-wise correlation, so the
-"groups" axis of the config is the channel width of its variance / adaptive aggregation.
+graph-captured launches, inputs resident), precision fp16.  The "groups" axis: the reference itself has no group-wise
+correlation -- its variance / adaptive aggregations are swept over the channel width C, and the
+group-wise correlation variant this package adds (csrc/warp_gwc.cu) over G in {4, 8, 16, 32} (G <= C).
 
-    python scripts/sweep_cost_volume.py [--out profiles/r01_sweep.json]
+    python scripts/sweep_cost_volume.py [--out profiles/r02_sweep.json]
 """
 import argparse
 import json
@@ -36,11 +37,11 @@ def timed(fn, reps=5):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_sweep.json"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_sweep.json"))
     ap.add_argument("--quick", action="store_true")
     args = ap.parse_args()
     import damvsnet_b200 as dm
-    dm.set_precision("bf16")   # measures the reduced-precision pipeline (the package default is fp32)
+    dm.set_precision("fp16")   # measures the reduced-precision pipeline (the package default is fp32)
     from damvsnet_b200 import ops, synthetic
     from damvsnet_b200.runner import HotPathRunner
     torch.set_grad_enabled(False)
@@ -68,10 +69,17 @@ def main():
             rt = net.stage_rot_trans(pm)
             nhwc = [ops.features_to_nhwc_half(f) for f in feats]
             wnet = net.weight_net[stage].folded()
-            vol = ops.warp_aggregate(nhwc[0], nhwc[1:], rt, dv, wnet, "adaptive", torch.bfloat16)
-            t_warp = timed(lambda: ops.warp_aggregate(nhwc[0], nhwc[1:], rt, dv, wnet, "adaptive", torch.bfloat16))
-            t_var = timed(lambda: ops.warp_aggregate(nhwc[0], nhwc[1:], rt, dv, None, "variance", torch.bfloat16))
-            b_warp = N * C * h * w * 4 + vox * 4 + vox * C * 2
+            vol = ops.warp_aggregate(nhwc[0], nhwc[1:], rt, dv, wnet, "adaptive", torch.float16)
+            t_warp = timed(lambda: ops.warp_aggregate(nhwc[0], nhwc[1:], rt, dv, wnet, "adaptive", torch.float16))
+            t_var = timed(lambda: ops.warp_aggregate(nhwc[0], nhwc[1:], rt, dv, None, "variance", torch.float16))
+            b_warp = N * C * h * w * 2 + vox * 4 + vox * C * 2        # fp16 features read, fp32 hypotheses, fp16 volume written
+            gwc = {}
+            for G in (4, 8, 16, 32):
+                if G > C:
+                    continue
+                t_g = timed(lambda: ops.warp_groupwise(nhwc[0], nhwc[1:], rt, dv, G, torch.float16))
+                b_g = N * C * h * w * 2 + vox * 4 + vox * max(G, 8) * 2
+                gwc[f"G{G}"] = {"ms": t_g, "GBps": b_g / t_g / 1e6, "hbm_frac": b_g / t_g / 1e6 / peaks["hbm_gbs"]}
             logits = cr.forward_g8(vol)
             t_reg = timed(lambda: cr.forward_g8(vol))
             chans = [(C, 8, 1.0), (8, 16, 1 / 8), (16, 16, 1 / 8), (16, 32, 1 / 64), (32, 32, 1 / 64), (32, 64, 1 / 512), (64, 64, 1 / 512),
@@ -81,14 +89,14 @@ def main():
             b_head = 2 * vox * 4 + vox * 4 + 3 * h * w * 4
             rows.append({"C": C, "D": D, "h": h, "w": w, "voxels": vox,
                          "warp_agg_adaptive_ms": t_warp, "warp_agg_adaptive_GBps": b_warp / t_warp / 1e6, "warp_agg_adaptive_hbm_frac": b_warp / t_warp / 1e6 / peaks["hbm_gbs"],
-                         "warp_agg_variance_ms": t_var, "warp_agg_variance_GBps": b_warp / t_var / 1e6,
+                         "warp_agg_variance_ms": t_var, "warp_agg_variance_GBps": b_warp / t_var / 1e6, "warp_gwc": gwc,
                          "costregnet_ms": t_reg, "costregnet_TFLOPs": flops / t_reg / 1e9, "costregnet_tensor_frac": flops / t_reg / 1e9 / peaks["bf16_tflops_sustained"],
                          "head_ms": t_head, "head_GBps": b_head / t_head / 1e6, "head_hbm_frac": b_head / t_head / 1e6 / peaks["hbm_gbs"]})
             r = rows[-1]
-            print(f"C={C:2d} D={D:3d} {h}x{w}: warp {t_warp:7.3f} ms ({r['warp_agg_adaptive_GBps']:6.0f} GB/s)  variance {t_var:7.3f}  costreg {t_reg:7.3f} ms ({r['costregnet_TFLOPs']:5.0f} TF/s)  head {t_head:6.3f} ms ({r['head_GBps']:5.0f} GB/s)", flush=True)
+            print(f"C={C:2d} D={D:3d} {h}x{w}: warp {t_warp:7.3f} ms ({r['warp_agg_adaptive_GBps']:6.0f} GB/s)  variance {t_var:7.3f}  gwc {' '.join(f'{k}:{v["ms"]:.3f}' for k, v in gwc.items())}  costreg {t_reg:7.3f} ms ({r['costregnet_TFLOPs']:5.0f} TF/s)  head {t_head:6.3f} ms ({r['head_GBps']:5.0f} GB/s)", flush=True)
             del vol, logits, feats, nhwc, dv
             torch.cuda.empty_cache()
-    json.dump({"peaks": peaks, "n_views": N, "precision": "bf16", "rows": rows}, open(args.out, "w"), indent=1)
+    json.dump({"peaks": peaks, "n_views": N, "precision": "fp16", "rows": rows}, open(args.out, "w"), indent=1)
 
 
 if __name__ == "__main__":
