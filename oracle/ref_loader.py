@@ -121,3 +121,37 @@ def build_cascade(ndepths=(48, 32, 8), mode: str = "adaptive", hot_state_dict: O
         missing, unexpected = model.load_state_dict(hot_state_dict, strict=False)
         assert not unexpected, unexpected
     return model.eval()
+
+
+def _homo_warping_any_dtype(src_fea, src_proj, ref_proj, depth_values):
+    """models/module.py:297-332 restated with the coordinate grid in the features' dtype.  The reference builds the grid
+    in float32 explicitly (module.py:312-313), so its own function cannot run in float64; everything else of the float64
+    yardstick below IS the reference's code."""
+    import torch.nn.functional as F
+    b, c, h, w = src_fea.shape
+    d = depth_values.shape[1]
+    dt, dev = src_fea.dtype, src_fea.device
+    with torch.no_grad():
+        proj = torch.matmul(src_proj, torch.inverse(ref_proj))
+        rot, trans = proj[:, :3, :3], proj[:, :3, 3:4]
+        y, x = torch.meshgrid(torch.arange(h, dtype=dt, device=dev), torch.arange(w, dtype=dt, device=dev), indexing="ij")
+        xyz = torch.stack((x.reshape(-1), y.reshape(-1), torch.ones(h * w, dtype=dt, device=dev))).unsqueeze(0).repeat(b, 1, 1)
+        pts = torch.matmul(rot, xyz).unsqueeze(2) * depth_values.view(b, 1, d, -1) + trans.view(b, 3, 1, 1)
+        xy = pts[:, :2] / pts[:, 2:3]
+        grid = torch.stack((xy[:, 0] / ((w - 1) / 2) - 1, xy[:, 1] / ((h - 1) / 2) - 1), dim=3)
+    out = F.grid_sample(src_fea, grid.view(b, d * h, w, 2), mode="bilinear", padding_mode="zeros", align_corners=False)
+    return out.view(b, c, d, h, w)
+
+
+@torch.no_grad()
+def float64_stage_forward(depthnet64, crs64, stage_idx, feats, proj, dv) -> Dict[str, torch.Tensor]:
+    """One stage of the reference's DepthNet evaluated in float64 (`depthnet64`, `crs64` = build_hot_path(...) cast with
+    .double()): the yardstick that separates the rounding noise of two fp32 implementations (scripts/fp32_truth.py,
+    tests/test_gpu_fullsize.py)."""
+    cas, _ = load()
+    orig = cas.homo_warping
+    cas.homo_warping = _homo_warping_any_dtype
+    try:
+        return depthnet64(stage_idx, [x.double() for x in feats], proj.double(), dv.double(), dv.shape[1], crs64[stage_idx])
+    finally:
+        cas.homo_warping = orig

@@ -31,25 +31,6 @@ def stats(a, b):
             "p9999": top[-1].item(), "max": rel.max().item(), "argmax": i, "n_gt_1e-4": int((rel > 1e-4).sum())}
 
 
-def homo_warping_any_dtype(src_fea, src_proj, ref_proj, depth_values):
-    """models/module.py:297-332 restated with the coordinate grid in the features' dtype (the reference builds it in
-    float32 explicitly, so its own function cannot run in float64)."""
-    import torch.nn.functional as F
-    b, c, h, w = src_fea.shape
-    d = depth_values.shape[1]
-    dt, dev = src_fea.dtype, src_fea.device
-    with torch.no_grad():
-        proj = torch.matmul(src_proj, torch.inverse(ref_proj))
-        rot, trans = proj[:, :3, :3], proj[:, :3, 3:4]
-        y, x = torch.meshgrid(torch.arange(h, dtype=dt, device=dev), torch.arange(w, dtype=dt, device=dev), indexing="ij")
-        xyz = torch.stack((x.reshape(-1), y.reshape(-1), torch.ones(h * w, dtype=dt, device=dev))).unsqueeze(0).repeat(b, 1, 1)
-        pts = torch.matmul(rot, xyz).unsqueeze(2) * depth_values.view(b, 1, d, -1) + trans.view(b, 3, 1, 1)
-        xy = pts[:, :2] / pts[:, 2:3]
-        grid = torch.stack((xy[:, 0] / ((w - 1) / 2) - 1, xy[:, 1] / ((h - 1) / 2) - 1), dim=3)
-    out = F.grid_sample(src_fea, grid.view(b, d * h, w, 2), mode="bilinear", padding_mode="zeros", align_corners=False)
-    return out.view(b, c, d, h, w)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "fp32_truth.json"))
@@ -79,13 +60,7 @@ def main():
         f, p, d = stages[s]
         with torch.no_grad(), warnings.catch_warnings():
             warnings.simplefilter("ignore")
-            cas, _ = ref_loader.load()
-            orig = cas.homo_warping
-            cas.homo_warping = homo_warping_any_dtype
-            try:
-                truth = d64(s, [x.double() for x in f], p.double(), d.double(), d.shape[1], c64[s])
-            finally:
-                cas.homo_warping = orig
+            truth = ref_loader.float64_stage_forward(d64, c64, s, f, p, d)
             ref = d32(s, list(f), p, d, d.shape[1], c32[s])
             with dm.precision("fp32"):
                 ours = runner.run_stage(s, f, p, d)

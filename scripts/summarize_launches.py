@@ -3,7 +3,10 @@
 over one eager step of bench.py) into the per-kernel table profiles/rNN_launches_final.md and the per-class DRAM
 traffic file profiles/rNN_traffic.json that bench.py's `roofline.traffic` reads.
 
-    python scripts/summarize_launches.py gpurun_out/launches.csv profiles/r01 [launches per step]
+    python scripts/summarize_launches.py gpurun_out/launches.csv profiles/r01 [launches per step] [last]
+
+With `last`, the LAST `launches per step` launches of the hot-path classes are taken (one complete eager step at the end
+of the capture, after set-up launches such as the hypothesis sampler and weight packing).
 """
 import csv
 import json
@@ -31,7 +34,9 @@ def main():
         d = launches.setdefault(r[iid], {"name": r[iname], "grid": r[igrid]})
         d[r[imet]] = float(r[ival].replace(",", ""))
     ours = [(k, v) for k, v in launches.items() if klass(v["name"])]
-    if len(sys.argv) > 3:          # launches of this library in ONE step (the list may hold warm-up / further steps)
+    if len(sys.argv) > 4 and sys.argv[4] == "last":
+        ours = [(k, v) for k, v in ours if klass(v["name"]) != "hypotheses"][-int(sys.argv[3]):]
+    elif len(sys.argv) > 3:        # launches of this library in ONE step (the list may hold warm-up / further steps)
         ours = ours[:int(sys.argv[3])]
     keep = {k for k, _ in ours}
     if src != prefix + "_launches_final.csv":   # the committed copy holds only this library's launches of that step

@@ -69,12 +69,23 @@ def _run(dm, sd, stages, prec, only=None):
     return outs
 
 
+def _frac_above(out, ref, thr=1e-4):
+    rel = (out["depth"].cpu().double() - ref["depth"].cpu().double()).abs() / ref["depth"].cpu().double().abs()
+    return (rel > thr).double().mean().item()
+
+
 def test_dtu_full_size_fp32_matches_oracle(dm, dtu):
+    """fp32 pipeline against the fp32 CPU oracle: relative depth error <= 1e-4 on >= 99.998 % of the pixels and
+    <= 2e-4 everywhere.  Two independent fp32 implementations are being compared: measured on B200, ONE stage-1 pixel of
+    115 200 sits at 1.1e-4, and the float64 yardstick (next test) shows 8.0e-5 of that is the reference side's own
+    rounding noise and 3.1e-5 this package's."""
     sd, stages, want = dtu
     outs = _run(dm, sd, stages, "fp32")
     for s, (o, w) in enumerate(zip(outs, want)):
         e = stage_errors(o, w, stages[s][2])
-        assert e["depth_rel_max"] <= 1e-4, (s, e)
+        assert e["depth_rel_max"] <= 2e-4, (s, e)
+        assert e["depth_rel_p99"] <= 5e-5, (s, e)
+        assert _frac_above(o, w) <= 2e-5, (s, _frac_above(o, w), e)
         assert e["prob_max"] <= 2e-3, (s, e)
         assert e["conf_frac_gt_2e-3"] <= 2e-3, (s, e)
         assert e["var_rel_p99"] <= 1e-3, (s, e)
@@ -125,10 +136,44 @@ def test_dtu_full_size_reference_itself_on_gpu_agrees(dm, dtu):
     ours = _run(dm, sd, stages, "fp32")
     for s in range(3):
         e_oracle = stage_errors(ref[s], want[s], stages[s][2])
-        assert e_oracle["depth_rel_max"] <= 1e-4, ("reference-on-GPU vs oracle", s, e_oracle)
+        assert e_oracle["depth_rel_max"] <= 2e-4 and _frac_above(ref[s], want[s]) <= 2e-5, ("reference-on-GPU vs oracle", s, e_oracle)
         e_ours = stage_errors(ours[s], {k: v for k, v in ref[s].items()}, stages[s][2])
-        assert e_ours["depth_rel_max"] <= 1e-4, ("ours vs reference-on-GPU", s, e_ours)
+        assert e_ours["depth_rel_max"] <= 2e-4 and _frac_above(ours[s], ref[s]) <= 2e-5, ("ours vs reference-on-GPU", s, e_ours)
         assert e_ours["prob_max"] <= 2e-3, (s, e_ours)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref was not staged with this tree")
+def test_dtu_full_size_fp32_against_float64_yardstick(dm, dtu):
+    """The north star's fp32 claim, made exact: the reference's DepthNet evaluated in FLOAT64 on the GPU is the truth;
+    this package's fp32 pipeline must be within 1e-4 relative depth of it EVERYWHERE, and no further from it than the
+    reference's own fp32 path is (measured: stage 1 max 6.4e-5 ours vs 8.0e-5 reference; stages 2/3 < 1e-6 both)."""
+    import warnings
+    sd, stages, _ = dtu
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        d32, c32 = ref_loader.build_hot_path(sd, "adaptive", device=DEV)
+        d64, c64 = ref_loader.build_hot_path(sd, "adaptive", device=DEV)
+        d64, c64 = d64.double(), c64.double()
+        ours = _run(dm, sd, stages, "fp32")
+        for s, (f, p, d) in enumerate(stages):
+            f, p, d = [x.to(DEV) for x in f], p.to(DEV), d.to(DEV)
+            with warnings.catch_warnings(), torch.no_grad():
+                warnings.simplefilter("ignore")
+                truth = ref_loader.float64_stage_forward(d64, c64, s, f, p, d)
+                ref = d32(s, list(f), p, d, d.shape[1], c32[s])
+            t = truth["depth"]
+            e_ours = ((ours[s]["depth"].double() - t).abs() / t.abs())
+            e_ref = ((ref["depth"].double() - t).abs() / t.abs())
+            assert e_ours.max().item() <= 1e-4, (s, e_ours.max().item())
+            assert e_ours.max().item() <= 1.5 * e_ref.max().item() + 1e-6, (s, e_ours.max().item(), e_ref.max().item())
+            assert e_ours.median().item() <= 1.5 * e_ref.median().item() + 1e-7, (s, e_ours.median().item(), e_ref.median().item())
+            assert (ours[s]["prob_volume"].double() - truth["prob_volume"]).abs().max().item() <= 1e-3
+            del truth, ref
+            torch.cuda.empty_cache()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
 def test_tnt_full_size_stage3_seven_views_matches_oracle(dm):
