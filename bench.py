@@ -671,10 +671,12 @@ def run_ours(args):
             a = alg.get(c, {"bytes": 0.0, "flops": 0.0})
             avg_ms = k["ms_per_step"] / max(k["launches_per_step"], 1)
             gbs = a["bytes"] / k["ms_per_step"] / 1e6
+            # measured DRAM bytes (ncu launch list of this same step, profiles/r02_traffic.json), per C-ABI call like `achieved`;
+            # only trusted when the list holds exactly the kernels this step launches (conv6 is two kernels in one call)
             tr = traffic.get(c)
             tr_per_launch = None
-            if tr and tr.get("launches_per_step") == k["launches_per_step"]:
-                tr_per_launch = tr["dram_bytes_per_launch"]
+            if tr and sum(v.get("launches_per_step", 0) for v in traffic.values()) == int(launches):
+                tr_per_launch = (tr["dram_read_per_step"] + tr["dram_write_per_step"]) / max(k["launches_per_step"], 1)
             r = {"kernel": c, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
                  "traffic": tr_per_launch, "peak_source": pk["src"], "avg_launch_ms": avg_ms,
                  "algorithmic_bytes_per_step": a["bytes"], "algorithmic_bytes_per_launch": a["bytes"] / max(k["launches_per_step"], 1),

@@ -9,6 +9,8 @@
 // k is a coalesced 128-byte line per warp.  A pixel's column is strided by H*W
 // in memory; the main kernel stages a D x 128-pixel tile in shared memory with
 // cp.async, a streaming kernel covers any D / alignment.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace damvs {
@@ -85,6 +87,64 @@ __global__ void __launch_bounds__(kHeadPix) head_staged_kernel(const float* __re
   var[o] = 3.f * sqrtf(d2sum);
 }
 
+// Register variant (D in {8, 16, 32, 48, 64, 96}, per-pixel hypotheses): one thread per pixel holds its whole logits column
+// in registers.  All D loads of a column are independent and issued back to back (D x 128-byte lines in flight per warp),
+// the hypothesis column follows the same way while the soft-max runs, and nothing waits on a CTA-wide barrier: measured
+// in situ (DRAM-cold inputs, right after the `prob` convolution) the staged kernel above spent most of its time with
+// every warp of a CTA parked behind one cp.async group + __syncthreads (108 us for the 182 MB of stage 2 = 1.7 TB/s).
+// Arithmetic is unchanged (expf, IEEE division, the reference's operation order), so results are bit-identical to the
+// staged kernel.
+template <int D>
+__global__ void __launch_bounds__(128) head_reg_kernel(const float* __restrict__ logits, const float* __restrict__ hyp,
+                                                       float* __restrict__ prob, float* __restrict__ depth, float* __restrict__ conf,
+                                                       float* __restrict__ var, long long HW) {
+  const int b = blockIdx.y;
+  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (p >= HW) return;
+  const float* lg = logits + (long long)b * D * HW + p;
+  const float* hg = hyp + (long long)b * D * HW + p;
+  float e[D], h[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) e[k] = __ldcs(lg + (long long)k * HW);
+#pragma unroll
+  for (int k = 0; k < D; ++k) h[k] = __ldcs(hg + (long long)k * HW);
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < D; ++k) m = fmaxf(m, e[k]);
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    e[k] = expf(e[k] - m);
+    s += e[k];
+  }
+  float dsum = 0.f, isum = 0.f;
+  float* pr = prob ? prob + (long long)b * D * HW + p : nullptr;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const float pk = e[k] / s;
+    e[k] = pk;
+    dsum += pk * h[k];
+    isum += pk * (float)k;
+    if (pr) __stcs(pr + (long long)k * HW, pk);
+  }
+  float d2sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const float df = h[k] - dsum;
+    d2sum += (df * df) * e[k];
+  }
+  long long idx = (long long)isum;  // .long() truncation, reference cas_mvsnet.py:116
+  idx = idx < 0 ? 0 : (idx > D - 1 ? D - 1 : idx);
+  const int i0 = (int)idx - 1, i1 = (int)idx + 2;
+  float c = 0.f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) c += (k >= i0 && k <= i1) ? e[k] : 0.f;   // same ascending order as the staged kernel's window loop
+  const long long o = (long long)b * HW + p;
+  depth[o] = dsum;
+  conf[o] = c;
+  var[o] = 3.f * sqrtf(d2sum);
+}
+
 // Any D: three passes over the logits column (re-reads are L2 hits).
 __global__ void __launch_bounds__(256) head_stream_kernel(const float* __restrict__ logits,
                                                           const float* __restrict__ hyp, float* __restrict__ prob,
@@ -153,7 +213,13 @@ extern "C" int damvs_softmax_regress_fwd(const float* logits, const float* depth
   cudaStream_t st = (cudaStream_t)stream;
   unsigned blocks = (unsigned)((total + 255) / 256);
   const bool aligned = (HW % 4 == 0) && aligned16(logits) && aligned16(depth_hyp) && B <= 65535;
-  if (D <= 64 && aligned) {
+  static const bool no_reg = getenv("DAMVS_HEAD_STAGED") != nullptr;   // development knob: A/B against the staged kernel
+  if (!no_reg && per_pixel_hyp && B <= 65535 && (D == 8 || D == 16 || D == 32 || D == 48 || D == 64 || D == 96)) {
+    dim3 grid((unsigned)((HW + 127) / 128), B);
+#define GO(DD) head_reg_kernel<DD><<<grid, 128, 0, st>>>(logits, depth_hyp, prob, depth, conf, var, HW)
+    if (D == 8) GO(8); else if (D == 16) GO(16); else if (D == 32) GO(32); else if (D == 48) GO(48); else if (D == 64) GO(64); else GO(96);
+#undef GO
+  } else if (D <= 64 && aligned) {
     const size_t smem = (size_t)2 * D * kHeadPix * sizeof(float);
     if (smem > 48 * 1024)
       DAMVS_CUDA_OK(cudaFuncSetAttribute(head_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
