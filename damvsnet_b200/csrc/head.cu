@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) head_reg_kernel(const float* __restrict__
                                                        float* __restrict__ prob, float* __restrict__ depth, float* __restrict__ conf,
                                                        float* __restrict__ var, long long HW) {
   const int b = blockIdx.y;
-  const long long p = (long long)blockIdx.x * 128 + threadIdx.x;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
   const float* lg = logits + (long long)b * D * HW + p;
   const float* hg = hyp + (long long)b * D * HW + p;
@@ -222,8 +222,10 @@ extern "C" int damvs_softmax_regress_fwd(const float* logits, const float* depth
   const bool aligned = (HW % 4 == 0) && aligned16(logits) && aligned16(depth_hyp) && B <= 65535;
   static const bool no_reg = getenv("DAMVS_HEAD_STAGED") != nullptr;   // development knob: A/B against the staged kernel
   if (!no_reg && per_pixel_hyp && B <= 65535 && (D == 8 || D == 16 || D == 32 || D == 48 || D == 64 || D == 96)) {
-    dim3 grid((unsigned)((HW + 127) / 128), B);
-#define GO(DD) head_reg_kernel<DD><<<grid, 128, 0, st>>>(logits, depth_hyp, prob, depth, conf, var, HW)
+    // small maps (stage 1: 115 k pixels) get 64-thread CTAs: twice the CTAs to spread over the 148 SMs
+    const int threads = total < 148ll * 8 * 128 ? 64 : 128;
+    dim3 grid((unsigned)((HW + threads - 1) / threads), B);
+#define GO(DD) head_reg_kernel<DD><<<grid, threads, 0, st>>>(logits, depth_hyp, prob, depth, conf, var, HW)
     if (D == 8) GO(8); else if (D == 16) GO(16); else if (D == 32) GO(32); else if (D == 48) GO(48); else if (D == 64) GO(64); else GO(96);
 #undef GO
   } else if (D <= 64 && aligned) {
