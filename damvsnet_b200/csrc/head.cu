@@ -69,8 +69,9 @@ __global__ void __launch_bounds__(kHeadPix) head_staged_kernel(const float* __re
   }
   float dsum = 0.f, isum = 0.f;
   float* pr = prob ? prob + (long long)b * D * HW + p0 + t : nullptr;
+  const float inv_s = 1.f / s;   // one IEEE division per pixel; p = e * (1 / s) (see head_reg_kernel)
   for (int k = 0; k < D; ++k) {
-    const float pk = sl[k * kHeadPix + t] / s;
+    const float pk = sl[k * kHeadPix + t] * inv_s;
     sl[k * kHeadPix + t] = pk;
     const float dk = per_pixel ? sh[k * kHeadPix + t] : __ldg(hb + k);
     dsum += pk * dk;
@@ -99,8 +100,8 @@ __global__ void __launch_bounds__(kHeadPix) head_staged_kernel(const float* __re
 // the hypothesis column follows the same way while the soft-max runs, and nothing waits on a CTA-wide barrier: measured
 // in situ (DRAM-cold inputs, right after the `prob` convolution) the staged kernel above spent most of its time with
 // every warp of a CTA parked behind one cp.async group + __syncthreads (108 us for the 182 MB of stage 2 = 1.7 TB/s).
-// Arithmetic is unchanged (expf, IEEE division, the reference's operation order), so results are bit-identical to the
-// staged kernel.
+// Arithmetic is the staged kernel's (expf, one IEEE reciprocal per pixel, the reference's operation order), so the two
+// kernels give bit-identical results.
 template <int D>
 __global__ void __launch_bounds__(128) head_reg_kernel(const float* __restrict__ logits, const float* __restrict__ hyp,
                                                        float* __restrict__ prob, float* __restrict__ depth, float* __restrict__ conf,
@@ -126,9 +127,13 @@ __global__ void __launch_bounds__(128) head_reg_kernel(const float* __restrict__
   }
   float dsum = 0.f, isum = 0.f;
   float* pr = prob ? prob + (long long)b * D * HW + p : nullptr;
+  // One IEEE division per pixel, then p = e * (1 / s): D divisions per pixel (FCHK + ~10 instructions each, plus the
+  // slow-path call) were a third of this kernel's instructions and kept stage 2 issue-bound (ncu: 92 warp instructions
+  // per hypothesis, issue slots 64 % busy, 2.9 TB/s).  The product differs from the quotient by at most one ulp.
+  const float inv_s = 1.f / s;
 #pragma unroll
   for (int k = 0; k < D; ++k) {
-    const float pk = e[k] / s;
+    const float pk = e[k] * inv_s;
     e[k] = pk;
     dsum += pk * h[k];
     isum += pk * (float)k;
@@ -171,8 +176,9 @@ __global__ void __launch_bounds__(256) head_stream_kernel(const float* __restric
   for (int k = 0; k < D; ++k) s += exp_clamped(__ldg(lg + (long long)k * HW) - m);
   float dsum = 0.f, isum = 0.f;
   float* pr = prob ? prob + b * D * HW + p : nullptr;
+  const float inv_s = 1.f / s;
   for (int k = 0; k < D; ++k) {
-    float pk = exp_clamped(__ldg(lg + (long long)k * HW) - m) / s;
+    float pk = exp_clamped(__ldg(lg + (long long)k * HW) - m) * inv_s;
     dsum += pk * __ldg(hp + k * hs);
     isum += pk * (float)k;
     if (pr) pr[(long long)k * HW] = pk;
@@ -181,7 +187,7 @@ __global__ void __launch_bounds__(256) head_stream_kernel(const float* __restric
   idx = idx < 0 ? 0 : (idx > D - 1 ? D - 1 : idx);
   float d2sum = 0.f, c = 0.f;
   for (int k = 0; k < D; ++k) {
-    float pk = exp_clamped(__ldg(lg + (long long)k * HW) - m) / s;
+    float pk = exp_clamped(__ldg(lg + (long long)k * HW) - m) * inv_s;
     float t = __ldg(hp + k * hs) - dsum;
     d2sum += (t * t) * pk;
     if (k >= idx - 1 && k <= idx + 2) c += pk;
