@@ -115,3 +115,52 @@ def test_two_rank_overlapped_stage_buckets_average_gradients():
         for a, b, ga, gb in zip(l0, l1, g0, g1):
             torch.testing.assert_close(ga, (a + b) / 2)
             torch.testing.assert_close(gb, (a + b) / 2)
+
+
+def _skew_worker(rank, world, port, ret):
+    """One rank's middle stage never gets a gradient (its hooks never complete that bucket): the collectives must still
+    pair up -- every rank issues them in the same order."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    stages = [torch.nn.Linear(4, 4) for _ in range(3)]
+    ob = training.OverlappedBuckets([list(m.parameters()) for m in stages])
+    for m in stages:
+        m.zero_grad(set_to_none=False)
+    x = torch.full((2, 4), float(rank + 1))
+    loss = stages[0](x).sum() + 3 * stages[2](x).sum()
+    if rank == 0:
+        loss = loss + 2 * stages[1](x).sum()              # rank 1: stage 1 takes no part in the loss
+    loss.backward()
+    local = [torch.zeros_like(p) if p.grad is None else p.grad.clone() for m in stages for p in m.parameters()]
+    ob.finish()
+    got = [p.grad.clone() for m in stages for p in m.parameters()]
+    # a second backward before finish() is refused instead of silently corrupting the averages
+    raised = False
+    (stages[0](x).sum() + stages[1](x).sum() + stages[2](x).sum()).backward()
+    try:
+        stages[2](x).sum().backward()
+    except RuntimeError as exc:
+        raised = "second backward" in str(exc)
+    ob.reset()
+    ob.close()
+    n_hooks_left = len(ob._handles)
+    stages[2](x).sum().backward()                            # hooks are gone: nothing fires, nothing raises
+    ret[rank] = (local, got, raised, n_hooks_left)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_overlapped_buckets_fixed_order_guard_and_close():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_skew_worker, args=(world, port, ret), nprocs=world, join=True)
+        (l0, g0, raised0, h0), (l1, g1, raised1, h1) = ret[0], ret[1]
+    for a, b, ga, gb in zip(l0, l1, g0, g1):
+        torch.testing.assert_close(ga, (a + b) / 2)
+        torch.testing.assert_close(gb, (a + b) / 2)
+    assert raised0 and raised1
+    assert h0 == 0 and h1 == 0
