@@ -549,7 +549,7 @@ def run_ours(args):
     for s, (fs, p, _) in enumerate(host_stages):
         b, _, h, w = fs[0].shape
         if s == 0:
-            dv = runner._range_hypotheses(depth_range, nd[s], b, h, w)
+            dv = runner.range_hypotheses(depth_range, nd[s], b, h, w)
         else:
             dv = dm.ops.stage_hypotheses(prev_maps[s][0].to(dev), prev_maps[s][1].to(dev), nd[s], args.height, args.width, args.height // h)
         dev_stages.append(([f.to(dev) for f in fs], p.to(dev), dv))

@@ -233,7 +233,7 @@ class HotPathRunner:
                 if isinstance(ddv, tuple):   # teacher-forced cascade: the previous stage's (depth, variance) maps were handed in
                     ddv = ops.stage_hypotheses(ddv[0], ddv[1], ndepths[i], height, width, height // h)
                 elif prev is None:          # plane-sweep range -> evenly spaced hypotheses (models/module.py:1003-1010)
-                    ddv = self._range_hypotheses(rng_host, ndepths[i], b, h, w)
+                    ddv = self.range_hypotheses(rng_host, ndepths[i], b, h, w)
                 else:
                     ddv = ops.stage_hypotheses(prev["depth"], prev["variance"], ndepths[i], height, width, height // h)
             out = self.run_stage(i, dfe, dpr, ddv)
@@ -252,7 +252,7 @@ class HotPathRunner:
         fin.record(d2h)
         return HostTicket(host, fin)
 
-    def _range_hypotheses(self, depth_range: torch.Tensor, ndepth: int, b: int, h: int, w: int) -> torch.Tensor:
+    def range_hypotheses(self, depth_range: torch.Tensor, ndepth: int, b: int, h: int, w: int) -> torch.Tensor:
         """First-stage hypotheses [B,D,h,w] from the plane-sweep range [B,Dtot] (reference models/module.py:1003-1010)."""
         rng = depth_range.to(self.device, non_blocking=True)
         lo, hi = rng[:, 0], rng[:, -1]

@@ -572,7 +572,7 @@ def test_host_pipeline_teacher_forced_cascade_uploads_maps_not_hypotheses(dm):
     dev_stages = []
     for s, (fs, p, _) in enumerate(host):
         b, _, h, w = fs[0].shape
-        dv = runner._range_hypotheses(rng, nds[s], b, h, w) if s == 0 else \
+        dv = runner.range_hypotheses(rng, nds[s], b, h, w) if s == 0 else \
             ops.stage_hypotheses(prev[s][0].to(dev()), prev[s][1].to(dev()), nds[s], H, W, H // h)
         dev_stages.append(([f.to(dev()) for f in fs], p.to(dev()), dv))
     for prec, fmt in (("fp32", "nchw_f32"), ("fp16", "nhwc_f16")):
