@@ -3,6 +3,7 @@ checkout in the build container).  CPU part: construction, state_dict layout, th
 (-m gpu): the reference's CascadeMVSNet.forward executed end to end with the hot path re-bound to this package."""
 import contextlib
 import io
+import os
 import warnings
 
 import pytest
@@ -156,3 +157,60 @@ def test_reference_cascade_forward_runs_on_the_native_hot_path(prec):
         assert rel.quantile(0.99).item() <= (2e-3 if prec == "fp32" else 2e-2), (k, rel.quantile(0.99).item())
         assert got[k]["prob_volume"].shape == want[k]["prob_volume"].shape
         assert torch.isfinite(got[k]["depth"]).all()
+
+
+@pytest.mark.gpu
+def test_config0_cascade_512x640_five_views_against_the_reference_on_cpu():
+    """BASELINE.json configs[0]: CascadeMVSNet forward, random init, DTU-train shape 512x640, N = 5, D = 48/32/8, batch 1,
+    fp32 -- the reference's own CPU-runnable case.  The reference runs on the CPU as it is; the same class with the hot
+    path re-bound by dropin.install("fp32") runs on the GPU (its FPN / GeoFeatureFusion in PyTorch on the GPU).  Stage 1
+    is teacher-forced up to the fp32 noise of the PyTorch feature extractor on two devices; stages 2/3 compound it
+    through depth, variance and GeoFeatureFusion, hence quantile bounds."""
+    import damvsnet_b200 as dm
+    from damvsnet_b200 import dropin, synthetic
+    cas, _ = ref_loader.load()
+    dev = torch.device("cuda:0")
+    H, W, N = 512, 640, 5
+    dropin.uninstall()
+    torch.manual_seed(0)
+    ref_model = _cascade(cas)
+    projs, intr = synthetic.make_cameras(1, N, H, W, seed=0)
+    dvals = synthetic.make_depth_range(1, 192)
+    for m in ref_model.modules():                       # BN calibration (SURVEY.md 0.5): one cumulative-average train pass
+        if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+            m.momentum = None
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ref_model = ref_model.to(dev).train()
+        with torch.no_grad(), warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+            warnings.simplefilter("ignore")
+            ref_model(synthetic.make_images(1, N, H, W, seed=11).to(dev), {k: v.to(dev) for k, v in projs.items()}, dvals.to(dev),
+                      {k: v.to(dev) for k, v in intr.items()})
+        ref_model = ref_model.cpu().eval()
+        imgs = synthetic.make_images(1, N, H, W, seed=0)
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad(), warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+            warnings.simplefilter("ignore")
+            want = ref_model(imgs, projs, dvals, intr)                      # the reference, on the CPU, untouched
+        dropin.install(precision="fp32")
+        try:
+            ours = _cascade(cas)
+            ours.load_state_dict(ref_model.state_dict(), strict=True)
+            ours = ours.to(dev).eval()
+            with torch.no_grad(), warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+                warnings.simplefilter("ignore")
+                got = ours(imgs.to(dev), {k: v.to(dev) for k, v in projs.items()}, dvals.to(dev), {k: v.to(dev) for k, v in intr.items()})
+        finally:
+            dropin.uninstall()
+            dm.set_precision("fp32")
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    assert got["stage1"]["depth"].shape == (1, 128, 160) and got["depth"].shape == (1, 512, 640)
+    rel1 = ((got["stage1"]["depth"].cpu() - want["stage1"]["depth"]).abs() / want["stage1"]["depth"].abs()).flatten()
+    assert rel1.quantile(0.999).item() <= 1e-4 and rel1.max().item() <= 1e-3, (rel1.quantile(0.999).item(), rel1.max().item())
+    for k in ("stage2", "stage3"):
+        rel = ((got[k]["depth"].cpu() - want[k]["depth"]).abs() / want[k]["depth"].abs()).flatten()
+        assert rel[:: max(1, rel.numel() // 2 ** 22)].quantile(0.99).item() <= 2e-3, (k, rel.quantile(0.99).item())
+        assert (got[k]["prob_volume"].sum(1) - 1).abs().max().item() < 1e-4
