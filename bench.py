@@ -689,6 +689,11 @@ def run_ours(args):
                                           "frac": tf / pk["tensor_sustained"], "frac_of_burst": tf / pk["tensor"],
                                           "peak_source": pk["src"] + " (sustained bf16)"}})
             return r
+        if "head" not in klass and "conv_head" in kernels:
+            # the head ran fused into CostRegNet's last layer: its bytes belong to the conv class, minus the logits that no
+            # longer travel (written as 2-byte elements in 8d's conv figure, read as fp32 in its head figure)
+            V = sum(d * h * w for (h, w, _, d) in stage_dims(args.height, args.width, nd))
+            alg["conv"]["bytes"] += alg["head"]["bytes"] - V * 4 - V * (4 if args.precision == "fp32" else 2)
         rooflines = [roof_of(c) for c in klass]
         roof = max(rooflines, key=lambda r: r["ms_per_step"])
 

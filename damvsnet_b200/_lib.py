@@ -43,6 +43,8 @@ _SIGNATURES = {
     "damvs_conv3d_pack_weight": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p]),
     "damvs_conv3d_fwd": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p]),
+    "damvs_prob_head_supported": (c_int, [POINTER(ConvDesc)]),
+    "damvs_prob_head_fwd": (c_int, [POINTER(ConvDesc)] + [c_void_p] * 8),
     "damvs_softmax_regress_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int,
                                           c_int, c_int, c_int, c_void_p]),
     "damvs_depth_regression_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

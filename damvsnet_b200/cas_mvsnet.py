@@ -88,7 +88,13 @@ class DepthNet(nn.Module):
         if not isinstance(cost_regularization, CostRegNet):
             raise TypeError("cost_regularization must be a damvsnet_b200 CostRegNet")
         volume = self.cost_volume(stage_idx, features, proj_matrices, depth_values)
-        logits = cost_regularization.forward_g8(volume)                       # [B,D,h,w] fp32
+        # inference with per-pixel hypotheses: the last conv layer and the head run as one launch where the shape allows
+        fuse = prob_volume_init is None and depth_values.dim() == 4
+        logits = cost_regularization.forward_g8(volume, head_hypotheses=depth_values if fuse else None)
+        if isinstance(logits, tuple):
+            prob, depth, conf, var = logits
+            return {"depth": depth, "photometric_confidence": conf, "variance": var,
+                    "prob_volume": prob, "depth_values": depth_values}
         if prob_volume_init is not None:                                       # dead in the reference (always None)
             logits = logits + prob_volume_init
         dv = depth_values

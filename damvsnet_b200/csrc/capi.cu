@@ -31,6 +31,9 @@ int conv3d_tc_launch(const damvs_conv3d_desc*, const void*, const void*, const f
 size_t conv3d_tc_packed_bytes(const damvs_conv3d_desc*);
 int conv3d_tc_pack(const damvs_conv3d_desc*, const float*, void*, cudaStream_t);
 
+bool conv3d_tcp_head_supported(const damvs_conv3d_desc*);
+int conv3d_tcp_head_launch(const damvs_conv3d_desc*, const void*, const void*, const float*, float*, float*, float*, float*, cudaStream_t);
+
 static int check_conv_desc(const damvs_conv3d_desc* d) {
   DAMVS_REQUIRE(d != nullptr, "conv3d: null descriptor");
   DAMVS_REQUIRE(d->B > 0 && d->B <= 65535 && d->Din > 0 && d->Hin > 0 && d->Win > 0, "conv3d: bad extent B=%d D=%d H=%d W=%d",
@@ -90,4 +93,21 @@ extern "C" int damvs_conv3d_fwd(const damvs_conv3d_desc* d, const void* in, cons
   return d->impl == DAMVS_CONV_TCGEN05
              ? conv3d_tc_launch(d, in, packed, scale, shift, skip, out, (cudaStream_t)stream)
              : conv3d_direct_launch(d, in, packed, scale, shift, skip, out, (cudaStream_t)stream);
+}
+
+extern "C" int damvs_prob_head_supported(const damvs_conv3d_desc* d) {
+  if (check_conv_desc(d) != DAMVS_OK) return 0;
+  return d->impl == DAMVS_CONV_TCGEN05 && conv3d_tcp_head_supported(d) ? 1 : 0;
+}
+
+extern "C" int damvs_prob_head_fwd(const damvs_conv3d_desc* d, const void* in, const void* packed, const float* depth_hyp, float* prob,
+                                   float* depth, float* conf, float* var, void* stream) {
+  int rc = check_conv_desc(d);
+  if (rc) return rc;
+  DAMVS_REQUIRE(in && packed && depth_hyp && prob && depth && conf && var, "prob_head: null pointer");
+  DAMVS_REQUIRE(aligned16(in) && aligned16(packed), "prob_head: in and packed must be 16-byte aligned");
+  if (!(d->impl == DAMVS_CONV_TCGEN05 && conv3d_tcp_head_supported(d)))
+    return set_error(DAMVS_ERR_UNSUPPORTED, "prob_head: needs the tcgen05 prob layer (Cin 8 -> 1, stride 1, plain_out, bf16 / fp16 volume) "
+                                             "with D %% 8 == 0 and D <= 64; use damvs_conv3d_fwd + damvs_softmax_regress_fwd otherwise");
+  return conv3d_tcp_head_launch(d, in, packed, depth_hyp, prob, depth, conf, var, (cudaStream_t)stream);
 }

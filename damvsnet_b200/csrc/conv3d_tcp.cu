@@ -58,9 +58,16 @@ struct Params {
   int B, D, H, W;
   int tiles_x, tiles_y, ntiles, dbg;
   uint32_t fmt_xor;   // 0 for bf16 operands; the A / B format bits of the instruction descriptor for fp16 (XOR turns them off)
+  // fused head (HEAD = true): per-pixel hypotheses in, probability volume and the three maps out; `out` is unused
+  const float* hyp;
+  float* prob;
+  float* depth;
+  float* conf;
+  float* var;
 };
 
 __device__ __forceinline__ float shfl_dn(uint32_t v, int d) { return __uint_as_float(__shfl_down_sync(0xffffffffu, v, d)); }
+constexpr size_t kSmemBase = 45 * 1024;   // offset of the fused head's logits buffer (>= the base kernel's footprint)
 constexpr int NG = 2;            // epilogue groups of four warps; group g drains the output planes with global index = g mod 4
 constexpr int THREADS = 64 + NG * 128;
 __device__ __forceinline__ void group_barrier(int g) {   // constant ids: a register id would reserve all 16 barriers
@@ -70,6 +77,16 @@ __device__ __forceinline__ void group_barrier(int g) {   // constant ids: a regi
   else asm volatile("bar.sync 4, 128;" ::: "memory");
 }
 
+// exp(x), x <= 0, argument clamped at -80: keeps e and e / s out of the denormal slow paths (see head.cu)
+__device__ __forceinline__ float exp_clamped_p(float x) { return expf(fmaxf(x, -80.f)); }
+
+// HEAD = true fuses the softmax / regression / confidence / variance head (head.cu; reference models/cas_mvsnet.py:105-124)
+// into the epilogue: the CTA owns all D output planes of its 6 x 30 pixels, so the logits go to shared memory ([D][8][32]
+// fp32) instead of HBM, and when a tile's last plane has been drained the eight epilogue warps turn into a one-thread-per-
+// pixel head (same arithmetic as head_reg_kernel) that reads the pixel's hypothesis column (prefetched into L2 at the start
+// of the tile), writes prob_volume and the three maps, and hands the buffer back.  The logits never reach HBM (2 x D*h*w*4
+// bytes and one launch per stage saved); the MMA / TMA warps keep running up to RING planes ahead meanwhile.
+template <bool HEAD>
 __global__ void __launch_bounds__(THREADS, 2) conv3d_tcp_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ Params P) {
   constexpr uint32_t DESC_HI = (128u >> 4) | (1u << 14);   // SBO = 128 B, descriptor version 1
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -81,6 +98,7 @@ __global__ void __launch_bounds__(THREADS, 2) conv3d_tcp_kernel(const __grid_con
   uint64_t* done = bars + NS;         // MMA -> TMA and epilogue: the iteration's MMAs have completed
   uint64_t* acc_empty = bars + 2 * NS; // epilogue -> MMA: a pair of accumulator slots drained and zeroed (8 warps)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + RING / 2);
+  float* sL = reinterpret_cast<float*>(smem + kSmemBase);   // HEAD: logits / probabilities of the tile, [D][8 rows][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const Header* hdr = reinterpret_cast<const Header*>(P.blob);
@@ -182,6 +200,19 @@ __global__ void __launch_bounds__(THREADS, 2) conv3d_tcp_kernel(const __grid_con
         valid[c] = pr < TH && lane < TW && yo < P.H && xo < P.W;
         op[c] = P.out + ((size_t)b * D + z0) * HW + (size_t)yo * P.W + xo;
       }
+      if (HEAD) {
+        // pull the tile's hypothesis columns into L2 while the planes are being computed: warp w <-> tile row w,
+        // lane <-> plane (two lanes per 32 planes cover the first and the last byte of the row's 120-byte segment)
+        const int wi = grp * 4 + q;
+        if (wi < TH && ty0 + wi < P.H) {
+          const float* hrow = P.hyp + ((size_t)b * D) * HW + (size_t)(ty0 + wi) * P.W;
+          const int xa = tx0, xe = min(tx0 + TW, P.W) - 1;
+          for (int k = lane; k < D; k += 32) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(hrow + (size_t)k * HW + xa));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(hrow + (size_t)k * HW + xe));
+          }
+        }
+      }
       for (int z = z0; z < D; z += NG) {
         const uint32_t gz = zb + z;
         const int sl = (int)((gz + 1) & (RING - 1));
@@ -213,10 +244,69 @@ __global__ void __launch_bounds__(THREADS, 2) conv3d_tcp_kernel(const __grid_con
         group_barrier(grp);
 #pragma unroll
         for (int c = 0; c < MC; ++c) {
-          if (valid[c]) *op[c] = u0[c] + xb[c * 256 + 64] + xb[c * 256 + 128 + 32];   // kh 1 of the next row, kh 2 of the one after
-          op[c] += (size_t)NG * HW;
+          const float v = u0[c] + xb[c * 256 + 64] + xb[c * 256 + 128 + 32];   // kh 1 of the next row, kh 2 of the one after
+          if (HEAD) {
+            sL[(z * 8 + c * 4 + q) * 32 + lane] = v;
+          } else {
+            if (valid[c]) *op[c] = v;
+            op[c] += (size_t)NG * HW;
+          }
         }
         buf ^= 1;
+      }
+      if (HEAD) {
+        asm volatile("bar.sync 5, 256;" ::: "memory");   // both groups: every logit of the tile is in shared memory
+        const int wi = grp * 4 + q, yo = ty0 + wi, xo = tx0 + lane;
+        if (wi < TH && lane < TW && yo < P.H && xo < P.W) {
+          float* col = sL + wi * 32 + lane;               // element k at col[k * 256]
+          const size_t pix = (size_t)yo * P.W + xo;
+          const float* hp = P.hyp + ((size_t)b * D) * HW + pix;
+          float m = -INFINITY;
+          for (int k = 0; k < D; ++k) m = fmaxf(m, col[k * 256]);
+          float s = 0.f;
+          for (int k = 0; k < D; ++k) {
+            const float e = exp_clamped_p(col[k * 256] - m);
+            col[k * 256] = e;
+            s += e;
+          }
+          const float inv_s = 1.f / s;
+          float dsum = 0.f, isum = 0.f;
+          float* pr = P.prob + ((size_t)b * D) * HW + pix;
+          for (int k0 = 0; k0 < D; k0 += 8) {             // D is a multiple of 8; eight independent loads in flight
+            float h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = __ldg(hp + (size_t)(k0 + j) * HW);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float pk = col[(k0 + j) * 256] * inv_s;
+              col[(k0 + j) * 256] = pk;
+              dsum += pk * h[j];
+              isum += pk * (float)(k0 + j);
+              __stcs(pr + (size_t)(k0 + j) * HW, pk);
+            }
+          }
+          float d2sum = 0.f;
+          for (int k0 = 0; k0 < D; k0 += 8) {
+            float h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) h[j] = __ldg(hp + (size_t)(k0 + j) * HW);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float df = h[j] - dsum;
+              d2sum += (df * df) * col[(k0 + j) * 256];
+            }
+          }
+          long long idx = (long long)isum;                // .long() truncation, reference cas_mvsnet.py:116
+          idx = idx < 0 ? 0 : (idx > D - 1 ? D - 1 : idx);
+          float cf = 0.f;
+          for (int k = (int)idx - 1; k <= (int)idx + 2; ++k)
+            if (k >= 0 && k < D) cf += col[k * 256];
+          const size_t o = (size_t)b * HW + pix;
+          P.depth[o] = dsum;
+          P.conf[o] = cf;
+          P.var[o] = 3.f * sqrtf(d2sum);
+        }
+        asm volatile("bar.sync 5, 256;" ::: "memory");   // the buffer may be overwritten by the next tile's planes
       }
     }
   }
@@ -259,6 +349,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 constexpr size_t kSmem = (size_t)NS * SLOT_BYTES + 2 * B_ROWS * 16 + NG * 2 * R0 * 2 * 32 * sizeof(float) + (2 * NS + RING / 2) * sizeof(uint64_t) + 16;
+static_assert(kSmem <= kSmemBase, "the fused head's logits buffer starts at kSmemBase");
+constexpr int kHeadMaxD = 64;   // D * 1 KB of logits per CTA: two CTAs per SM up to D = 64
 
 }  // namespace tcp
 
@@ -279,10 +371,10 @@ int conv3d_tcp_pack(const damvs_conv3d_desc* d, const float* weight, void* packe
   return DAMVS_OK;
 }
 
-int conv3d_tcp_launch(const damvs_conv3d_desc* d, const void* in, const void* packed, void* out, cudaStream_t st) {
+template <bool HEAD>
+static int tcp_launch_impl(const damvs_conv3d_desc* d, const void* in, const void* packed, tcp::Params P, cudaStream_t st) {
   using namespace tcp;
-  Params P{};
-  P.blob = (const uint8_t*)packed; P.out = (float*)out;
+  P.blob = (const uint8_t*)packed;
   P.B = d->B; P.D = d->Din; P.H = d->Hin; P.W = d->Win;
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(DAMVS_ERR_CUDA, "cuTensorMapEncodeTiled entry point not found");
@@ -296,9 +388,10 @@ int conv3d_tcp_launch(const damvs_conv3d_desc* d, const void* in, const void* pa
   CUresult r = fn(&m0, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(in), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(DAMVS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  const size_t smem = kSmem;
-  DAMVS_CUDA_OK(cudaFuncSetAttribute(conv3d_tcp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  DAMVS_CUDA_OK(cudaFuncSetAttribute(conv3d_tcp_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  const size_t smem = HEAD ? kSmemBase + (size_t)d->Din * 8 * 32 * sizeof(float) : kSmem;
+  auto kern = conv3d_tcp_kernel<HEAD>;
+  DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DAMVS_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   static const int dbg = getenv("DAMVS_TCP_DBG") ? atoi(getenv("DAMVS_TCP_DBG")) : 0;   // development knob: 1 = no MMAs, 2 = no epilogue work
   P.dbg = dbg;
   P.tiles_x = (d->Win + TW - 1) / TW;
@@ -307,9 +400,29 @@ int conv3d_tcp_launch(const damvs_conv3d_desc* d, const void* in, const void* pa
   const int num_sms = current_sm_count();
   static const int occ_cap = getenv("DAMVS_TC_OCC") ? atoi(getenv("DAMVS_TC_OCC")) : 2;   // development knob
   dim3 grid((unsigned)std::min(P.ntiles, std::min(2, occ_cap) * num_sms), 1, 1);
-  conv3d_tcp_kernel<<<grid, THREADS, smem, st>>>(m0, P);
-  DAMVS_LAUNCH_OK("conv3d_tcp kernel");
+  kern<<<grid, THREADS, smem, st>>>(m0, P);
+  DAMVS_LAUNCH_OK(HEAD ? "conv3d_tcp kernel (fused head)" : "conv3d_tcp kernel");
   return DAMVS_OK;
+}
+
+int conv3d_tcp_launch(const damvs_conv3d_desc* d, const void* in, const void* packed, void* out, cudaStream_t st) {
+  tcp::Params P{};
+  P.out = (float*)out;
+  return tcp_launch_impl<false>(d, in, packed, P, st);
+}
+
+// prob convolution + softmax / regression / confidence / variance head in one launch (even D <= 64, D % 8 == 0)
+bool conv3d_tcp_head_supported(const damvs_conv3d_desc* d) {
+  static const bool off = getenv("DAMVS_NO_PROB_HEAD") != nullptr;   // development knob: A/B against the two-kernel path
+  return !off && conv3d_tcp_supported(d) && d->Din % 8 == 0 && d->Din <= tcp::kHeadMaxD &&
+         (d->in_dtype == DAMVS_BF16 || d->in_dtype == DAMVS_F16);
+}
+
+int conv3d_tcp_head_launch(const damvs_conv3d_desc* d, const void* in, const void* packed, const float* hyp, float* prob, float* depth,
+                           float* conf, float* var, cudaStream_t st) {
+  tcp::Params P{};
+  P.hyp = hyp; P.prob = prob; P.depth = depth; P.conf = conf; P.var = var;
+  return tcp_launch_impl<true>(d, in, packed, P, st);
 }
 
 }  // namespace damvs

@@ -380,6 +380,38 @@ def conv3d(vol: G8Volume, packed: torch.Tensor, scale: Optional[torch.Tensor], s
     return result
 
 
+def prob_head_supported(vol: G8Volume, impl: int) -> bool:
+    """Whether the `prob` layer + head of this volume can run as one launch (damvs_prob_head_fwd)."""
+    b, cin, d, h, w = vol.shape
+    if impl != CONV_TCGEN05 or cin != 8 or vol.dtype not in HALF_DTYPES:
+        return False
+    desc = conv_desc(b, cin, 1, d, h, w, 1, False, False, vol.dtype, torch.float32, True, impl)
+    return bool(_lib.load().damvs_prob_head_supported(ctypes.byref(desc)))
+
+
+def prob_head(vol: G8Volume, packed: torch.Tensor, depth_values: torch.Tensor, impl: int):
+    """CostRegNet's `prob` convolution fused with the head: G8 volume [B,8,D,H,W] + per-pixel hypotheses [B,D,H,W] ->
+    (prob_volume [B,D,H,W], depth, confidence, variance [B,H,W]); the logits never reach HBM."""
+    b, cin, d, h, w = vol.shape
+    _need(depth_values, "depth_values", torch.float32, 4)
+    if tuple(depth_values.shape) != (b, d, h, w):
+        raise ValueError(f"depth_values shape {tuple(depth_values.shape)} does not match [B={b},D={d},H={h},W={w}]")
+    dv = depth_values.contiguous()
+    desc = conv_desc(b, cin, 1, d, h, w, 1, False, False, vol.dtype, torch.float32, True, impl)
+    dev = vol.data.device
+    prob = torch.empty((b, d, h, w), dtype=torch.float32, device=dev)
+    depth = torch.empty((b, h, w), dtype=torch.float32, device=dev)
+    conf = torch.empty_like(depth)
+    var = torch.empty_like(depth)
+    flops = 2.0 * 27 * cin * b * d * h * w
+    nbytes = vol.data.numel() * vol.data.element_size() + 2 * dv.numel() * 4 + 3 * b * h * w * 4
+    detail = f"conv_head {cin}->1 s1 + head in {d}x{h}x{w}"
+    with torch.cuda.device_of(vol.data), _timed("conv_head", bytes=float(nbytes), flops=flops, detail=detail):
+        _lib.check(_lib.load().damvs_prob_head_fwd(ctypes.byref(desc), _p(vol.data), _p(packed), _p(dv), _p(prob), _p(depth), _p(conf),
+                                                   _p(var), _stream()))
+    return prob, depth, conf, var
+
+
 def softmax_regress(logits: torch.Tensor, depth_values: torch.Tensor, want_prob: bool = True):
     """logits [B,D,H,W] -> (prob [B,D,H,W] | None, depth, confidence, variance [B,H,W])."""
     _need(logits, "logits", torch.float32, 4)

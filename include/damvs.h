@@ -142,6 +142,17 @@ int damvs_warp_gwc_fwd(const void* ref_nhwc, const void* const* src_nhwc, int n_
                        const float* depth_hyp, void* out_vol, int B, int C, int G, int D, int H, int W,
                        int per_pixel_hyp, int feat_dtype, int out_dtype, void* stream);
 
+/* ---- fused `prob` convolution + head ------------------------------------------
+ * CostRegNet's last layer (models/module.py:530: Conv3d 8 -> 1, k3, p1, no bias) and the softmax / regression /
+ * confidence / variance head (models/cas_mvsnet.py:105-124) in ONE launch: the logits stay in shared memory.
+ * desc as for damvs_conv3d_fwd with plain_out = 1, impl = DAMVS_CONV_TCGEN05; packed = the same blob damvs_conv3d_fwd
+ * takes for that layer.  depth_hyp, prob: device fp32 [B][D][H][W]; depth, conf, var: device fp32 [B][H][W].
+ * damvs_prob_head_supported(desc) != 0 iff the shape qualifies (bf16 / fp16 volume, D % 8 == 0, D <= 64); otherwise
+ * call damvs_conv3d_fwd + damvs_softmax_regress_fwd.                                                              */
+int damvs_prob_head_supported(const damvs_conv3d_desc* desc);
+int damvs_prob_head_fwd(const damvs_conv3d_desc* desc, const void* in, const void* packed, const float* depth_hyp,
+                        float* prob, float* depth, float* conf, float* var, void* stream);
+
 /* ---- softmax / regression head -------------------------------------------- */
 /* Replaces models/cas_mvsnet.py:105-124 + depth_regression (models/module.py:609):
  * softmax over D, expected depth, photometric confidence (sum of p over

@@ -145,3 +145,53 @@ def test_cost_reg_net_tc_vs_direct_bf16(stage, prec):
     k = 1.0 if prec == "bf16" else 0.125
     assert (a - b).abs().max().item() < 3e-2 * k * max(scale, 1.0), ((a - b).abs().max().item(), scale)
     assert (a - b).abs().mean().item() < 3e-3 * k * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("shape", [
+    (1, 8, 13, 45),        # ragged tiles, one plane pair group
+    (2, 32, 20, 70),       # batch 2, stage-2 depth
+    (1, 48, 37, 61),       # stage-1 depth: the accumulator ring wraps many times per tile
+    (1, 8, 126, 330),      # more tiles than resident CTAs: the logits buffer is reused tile after tile
+    (1, 64, 9, 33),        # the largest fused depth
+])
+def test_fused_prob_head_matches_the_two_kernel_path(shape, prec):
+    """damvs_prob_head_fwd (prob convolution + softmax / regression / confidence / variance in one launch, logits in
+    shared memory) against damvs_conv3d_fwd + damvs_softmax_regress_fwd on the same volume: same MMAs, same head
+    arithmetic in the same order."""
+    import damvsnet_b200 as dm
+    from damvsnet_b200 import ops
+    hd = HALF[prec]
+    b, d, h, w = shape
+    g = torch.Generator().manual_seed(d * 7 + h)
+    wgt = _bf(torch.randn(1, 8, 3, 3, 3, generator=g) * 0.6, hd)
+    x = _bf(torch.randn(b, 8, d, h, w, generator=g), hd)
+    dv = (425 + 2.65 * torch.arange(d, dtype=torch.float32).view(1, d, 1, 1) + torch.rand(b, 1, h, w, generator=g)).expand(b, d, h, w).contiguous()
+    packed = ops.conv3d_pack_weight(wgt.to(dev()), 8, 1, False, ops.CONV_TCGEN05, 1, hd)
+    vol = dm.G8Volume.from_ncdhw(x.to(dev()), hd)
+    assert ops.prob_head_supported(vol, ops.CONV_TCGEN05)
+    logits = ops.conv3d(vol, packed, None, None, 1, 1, False, False, None, torch.float32, True, ops.CONV_TCGEN05)
+    want = ops.softmax_regress(logits, dv.to(dev()))
+    got = ops.prob_head(vol, packed, dv.to(dev()), ops.CONV_TCGEN05)
+    torch.cuda.synchronize()
+    for name, a, b_ in zip(("prob", "depth", "conf", "var"), got, want):
+        assert a.shape == b_.shape, name
+        assert torch.isfinite(a).all(), name
+        tol = 1e-6 if name == "prob" else 1e-5
+        assert (a - b_).abs().max().item() <= tol * max(1.0, b_.abs().max().item()), (name, (a - b_).abs().max().item())
+    # and against torch on the CPU (fp32 conv of the same rounded operands + the oracle's head)
+    import torch.nn.functional as F
+    from oracle import damvs_oracle as O
+    ref = O.regress_head(F.conv3d(x, wgt, None, padding=1).squeeze(1), dv)
+    assert (got[0].cpu() - ref["prob_volume"]).abs().max() < 1e-4
+    assert ((got[1].cpu() - ref["depth"]).abs() / ref["depth"].abs()).max() < 1e-4
+
+
+def test_fused_prob_head_falls_back_where_it_does_not_apply():
+    import damvsnet_b200 as dm
+    from damvsnet_b200 import ops
+    for d, ok in ((8, True), (6, False), (72, False)):        # D % 8 != 0 and D > 64 keep the two-kernel path
+        vol = dm.G8Volume(torch.zeros(1, 1, d, 8, 32, 8, device=dev(), dtype=torch.float16))
+        assert ops.prob_head_supported(vol, ops.CONV_TCGEN05) == ok, d
+    vol32 = dm.G8Volume(torch.zeros(1, 1, 8, 8, 32, 8, device=dev(), dtype=torch.float32))
+    assert not ops.prob_head_supported(vol32, ops.CONV_DIRECT)
