@@ -244,11 +244,11 @@ __global__ void __launch_bounds__(THREADS, 2) conv3d_tcp_kernel(const __grid_con
         group_barrier(grp);
 #pragma unroll
         for (int c = 0; c < MC; ++c) {
-          const float v = u0[c] + xb[c * 256 + 64] + xb[c * 256 + 128 + 32];   // kh 1 of the next row, kh 2 of the one after
+          // kh 1 of the next row, kh 2 of the one after; patch rows 6, 7 have no output (and nothing to read beyond them)
           if (HEAD) {
-            sL[(z * 8 + c * 4 + q) * 32 + lane] = v;
+            if (c * 4 + q < TH) sL[(z * 8 + c * 4 + q) * 32 + lane] = u0[c] + xb[c * 256 + 64] + xb[c * 256 + 128 + 32];
           } else {
-            if (valid[c]) *op[c] = v;
+            if (valid[c]) *op[c] = u0[c] + xb[c * 256 + 64] + xb[c * 256 + 128 + 32];
             op[c] += (size_t)NG * HW;
           }
         }
