@@ -70,6 +70,7 @@ def parse(argv=None):
     ap.add_argument("--budget-s", type=float, default=150.0, help="--impl reference: wall-clock budget of the timed passes")
     ap.add_argument("--detail", action="store_true", help="print a per-layer device-time table to stderr")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--fuse-prob-head", action="store_true", help="run CostRegNet's last layer fused with the head (one launch)")
     ap.add_argument("--inflight", type=int, default=4, help="independent views in flight on separate streams (graph mode)")
     return ap.parse_args(argv)
 
@@ -535,6 +536,7 @@ def run_ours(args):
     from damvsnet_b200.runner import HotPathRunner, ViewPipeline, make_workload
     _lib.check(_lib.load().damvs_check_device(local))
     dm.set_precision(args.precision, args.conv_impl)
+    dm.ops.set_fusion(prob_head=args.fuse_prob_head)
     nd = [int(x) for x in args.ndepths.split(",")]
     sd = synthetic.hot_path_state_dict(seed=0, mode=args.mode)
     runner = HotPathRunner(sd, mode=args.mode, device=dev)

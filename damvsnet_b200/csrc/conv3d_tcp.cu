@@ -413,8 +413,7 @@ int conv3d_tcp_launch(const damvs_conv3d_desc* d, const void* in, const void* pa
 
 // prob convolution + softmax / regression / confidence / variance head in one launch (even D <= 64, D % 8 == 0)
 bool conv3d_tcp_head_supported(const damvs_conv3d_desc* d) {
-  static const bool off = getenv("DAMVS_NO_PROB_HEAD") != nullptr;   // development knob: A/B against the two-kernel path
-  return !off && conv3d_tcp_supported(d) && d->Din % 8 == 0 && d->Din <= tcp::kHeadMaxD &&
+  return conv3d_tcp_supported(d) && d->Din % 8 == 0 && d->Din <= tcp::kHeadMaxD &&
          (d->in_dtype == DAMVS_BF16 || d->in_dtype == DAMVS_F16);
 }
 

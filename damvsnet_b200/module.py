@@ -240,8 +240,8 @@ class CostRegNet(_EpochOnApply):
     def forward_g8(self, vol: G8Volume, head_hypotheses: Optional[torch.Tensor] = None):
         """G8 cost volume -> logits [B,D,H,W] fp32 (the squeeze(1) of the reference output).
 
-        With `head_hypotheses` = per-pixel depth_values [B,D,H,W] (inference only), the last layer runs fused with the
-        softmax / regression head when the shape qualifies (ops.prob_head_supported) and the call returns the tuple
+        With `head_hypotheses` = per-pixel depth_values [B,D,H,W] (inference only) and ops.set_fusion(prob_head=True),
+        the last layer runs fused with the softmax / regression head when the shape qualifies and the call returns the tuple
         (prob_volume, depth, photometric_confidence, variance) instead of logits -- callers check the type."""
         b, c, d, h, w = vol.shape
         if c != self.in_channels:
@@ -258,8 +258,8 @@ class CostRegNet(_EpochOnApply):
         if ag.wants_grad(x.data, self.prob.weight):
             return ag.ProbConvFn.apply(x.data, self.prob.weight, self)
         impl = ops.conv_impl_for(self.base_channels, 1, 1, False)
-        if head_hypotheses is not None and head_hypotheses.dim() == 4 and not head_hypotheses.requires_grad \
-                and ops.prob_head_supported(x, impl):
+        if ops.fuse_prob_head() and head_hypotheses is not None and head_hypotheses.dim() == 4 \
+                and not head_hypotheses.requires_grad and ops.prob_head_supported(x, impl):
             return ops.prob_head(x, self._prob_prepared(impl, x.dtype), head_hypotheses, impl)
         return ops.conv3d(x, self._prob_prepared(impl, x.dtype), None, None, 1, 1, False, False, None, torch.float32, True, impl)
 

@@ -25,7 +25,7 @@ from ._lib import AGG_ADAPTIVE, AGG_VARIANCE, BF16, CONV_DIRECT, CONV_TCGEN05, F
 #   'fp16'  fp16 features, fp16 cost volume / activations / weights, tcgen05 convolutions, fp32 accumulation.  Inference.
 #           11 significand bits: 8x finer than bf16 at the same width and tensor-core rate.
 #   'bf16'  the same with bf16 volumes / activations / weights: the exponent range training gradients need.
-_POLICY = {"precision": "fp32", "conv_impl": "auto", "features": "auto"}
+_POLICY = {"precision": "fp32", "conv_impl": "auto", "features": "auto", "fuse_prob_head": False}
 
 
 def get_precision() -> str:
@@ -52,6 +52,17 @@ def precision(precision: str, conv_impl: str = "auto", features: str = "auto"):
         yield
     finally:
         _POLICY.update(old)
+
+
+def set_fusion(prob_head: bool) -> None:
+    """Opt into the fused `prob` convolution + head launch (damvs_prob_head_fwd).  Off by default: measured on B200 it
+    removes 0.28 GB of logits traffic and three launches per view but is no faster -- the head pass sits on the epilogue
+    warps' critical path -- so the two-kernel path stays the default."""
+    _POLICY["fuse_prob_head"] = bool(prob_head)
+
+
+def fuse_prob_head() -> bool:
+    return _POLICY["fuse_prob_head"]
 
 
 def half_features() -> bool:

@@ -506,6 +506,32 @@ def test_packed_weight_cache_follows_data_writes_after_invalidate(dm):
         assert not torch.allclose(cr(x), y0)
 
 
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+def test_depthnet_with_fused_prob_head_equals_the_two_kernel_path(dm, prec):
+    """ops.set_fusion(prob_head=True): DepthNet output dict from the fused last-layer + head launch against the default
+    two-kernel path, all three stages of the fixture."""
+    from damvsnet_b200 import _lib, ops
+    sd, stages = golden_io.load_depthnet("adaptive")
+    for stage, st in enumerate(stages):
+        net, cr = _build_net(dm, sd, stage, "adaptive")
+        args = ([f.to(dev()) for f in st["features"]], st["proj"].to(dev()), st["depth_values"].to(dev()), st["depth_values"].shape[1], cr)
+        with dm.precision(prec), torch.no_grad():
+            n0 = _lib.launch_count()
+            want = net(stage, *args)
+            n1 = _lib.launch_count()
+            ops.set_fusion(prob_head=True)
+            try:
+                got = net(stage, *args)
+            finally:
+                ops.set_fusion(prob_head=False)
+            n2 = _lib.launch_count()
+        assert (n2 - n1) == (n1 - n0) - 1                                  # one launch fewer
+        assert set(got) == set(want)
+        for k in ("depth", "photometric_confidence", "variance", "prob_volume"):
+            tol = 1e-6 if k == "prob_volume" else 1e-5
+            assert (got[k] - want[k]).abs().max().item() <= tol * max(1.0, want[k].abs().max().item()), (stage, k)
+
+
 def test_tanks_and_temples_shape_seven_views_invariants(dm):
     """BASELINE.json configs[2] (1056x1920, N=7, D=48/32/8) at full size, where the oracle is too slow: size-independent
     properties of the three stages in the benchmarked bf16 mode -- probabilities sum to one, the regressed depth lies
