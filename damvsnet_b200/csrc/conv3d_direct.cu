@@ -25,6 +25,12 @@ struct ConvParams {
   int B, Cin, Cout, Din, Hin, Win, Dout, Hout, Wout, stride, transposed, relu, plain_out;
 };
 
+// VX consecutive output voxels along x per thread: every weight vector read from shared memory feeds 8 * VX FMAs instead
+// of 8 (the one-voxel version issued one LDS.128 per four FMAs and ran at 24 % of the fp32 peak).  Each output's own
+// arithmetic -- tap order (kd, kh, kw), channels in order inside a tap, two-level summation -- is unchanged, so the
+// results are bit-identical to the one-voxel kernel.
+constexpr int kVX = 4;
+
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(128) conv3d_direct_kernel(const ConvParams P) {
   extern __shared__ float s_w[];  // [27][Cin][8]
@@ -36,17 +42,22 @@ __global__ void __launch_bounds__(128) conv3d_direct_kernel(const ConvParams P) 
     *reinterpret_cast<float4*>(s_w + i) = __ldg(reinterpret_cast<const float4*>(wsrc + i));
   __syncthreads();
 
+  const int Wq = (P.Wout + kVX - 1) / kVX;                 // x quads per output row
+  const long long HWq = (long long)P.Hout * Wq;
+  const long long Vq = HWq * P.Dout;
   const long long HWo = (long long)P.Hout * P.Wout;
   const long long Vo = HWo * P.Dout;
-  long long vox = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (vox >= Vo) return;
-  const int z = (int)(vox / HWo);
-  const int rem = (int)(vox - (long long)z * HWo);
-  const int y = rem / P.Wout, x = rem - y * P.Wout;
+  const long long vq = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vq >= Vq) return;
+  const int z = (int)(vq / HWq);
+  const int rem = (int)(vq - (long long)z * HWq);
+  const int y = rem / Wq, x0 = (rem - y * Wq) * kVX;
 
-  float acc[8];
+  float acc[kVX][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int v = 0; v < kVX; ++v)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[v][j] = 0.f;
 
   const TIn* in = reinterpret_cast<const TIn*>(P.in);
   for (int kd = 0; kd < 3; ++kd) {
@@ -70,65 +81,96 @@ __global__ void __launch_bounds__(128) conv3d_direct_kernel(const ConvParams P) 
       }
       if (yi < 0 || yi >= P.Hin) continue;
       for (int kw = 0; kw < 3; ++kw) {
-        int xi;
-        if (P.transposed) {
-          int num = x + 1 - kw;
-          if (num & 1) continue;
-          xi = num >> 1;
-        } else {
-          xi = x * P.stride - 1 + kw;
+        int xi[kVX];
+        bool ok[kVX], any = false;
+#pragma unroll
+        for (int v = 0; v < kVX; ++v) {
+          const int x = x0 + v;
+          if (P.transposed) {
+            const int num = x + 1 - kw;
+            xi[v] = num >> 1;
+            ok[v] = !(num & 1);
+          } else {
+            xi[v] = x * P.stride - 1 + kw;
+            ok[v] = true;
+          }
+          ok[v] = ok[v] && x < P.Wout && xi[v] >= 0 && xi[v] < P.Win;
+          any = any || ok[v];
         }
-        if (xi < 0 || xi >= P.Win) continue;
+        if (!any) continue;
         const float* wt = s_w + ((kd * 3 + kh) * 3 + kw) * Cin * 8;
         // two-level summation: the Cin products of one tap go into a fresh partial, the <= 27 partials into acc.  The
-        // rounding error grows with sqrt(Cin) + sqrt(27) instead of sqrt(27 * Cin) (up to 1728 terms) -- at the full
-        // DTU-test size the plain running sum left the worst of 115 k stage-1 pixels at 1.1e-4 relative depth error.
-        float part[8];
+        // rounding error grows with sqrt(Cin) + sqrt(27) instead of sqrt(27 * Cin) (up to 1728 terms).
+        float part[kVX][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) part[j] = 0.f;
+        for (int v = 0; v < kVX; ++v)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) part[v][j] = 0.f;
         for (int gi = 0; gi < Gin; ++gi) {
-          F8 v = load8(in + g8_offset(b, gi, zi, yi, xi, Gin, P.Din, P.Hin, P.Win));
+          F8 val[kVX];
+#pragma unroll
+          for (int v = 0; v < kVX; ++v) {
+            if (ok[v]) {
+              val[v] = load8(in + g8_offset(b, gi, zi, yi, xi[v], Gin, P.Din, P.Hin, P.Win));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) val[v].v[j] = 0.f;
+            }
+          }
 #pragma unroll
           for (int ci = 0; ci < 8; ++ci) {
             const float4 wa = *reinterpret_cast<const float4*>(wt + (gi * 8 + ci) * 8);
             const float4 wb = *reinterpret_cast<const float4*>(wt + (gi * 8 + ci) * 8 + 4);
-            part[0] = fmaf(v.v[ci], wa.x, part[0]);
-            part[1] = fmaf(v.v[ci], wa.y, part[1]);
-            part[2] = fmaf(v.v[ci], wa.z, part[2]);
-            part[3] = fmaf(v.v[ci], wa.w, part[3]);
-            part[4] = fmaf(v.v[ci], wb.x, part[4]);
-            part[5] = fmaf(v.v[ci], wb.y, part[5]);
-            part[6] = fmaf(v.v[ci], wb.z, part[6]);
-            part[7] = fmaf(v.v[ci], wb.w, part[7]);
+#pragma unroll
+            for (int v = 0; v < kVX; ++v) {
+              const float a = val[v].v[ci];
+              part[v][0] = fmaf(a, wa.x, part[v][0]);
+              part[v][1] = fmaf(a, wa.y, part[v][1]);
+              part[v][2] = fmaf(a, wa.z, part[v][2]);
+              part[v][3] = fmaf(a, wa.w, part[v][3]);
+              part[v][4] = fmaf(a, wb.x, part[v][4]);
+              part[v][5] = fmaf(a, wb.y, part[v][5]);
+              part[v][6] = fmaf(a, wb.z, part[v][6]);
+              part[v][7] = fmaf(a, wb.w, part[v][7]);
+            }
           }
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += part[j];
+        for (int v = 0; v < kVX; ++v)
+          if (ok[v]) {           // a tap that does not exist for this voxel contributes nothing (not even +0: -0 stays -0)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[v][j] += part[v][j];
+          }
       }
     }
   }
 
-  F8 r;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    int co = g * 8 + j;
-    float v = acc[j];
-    if (P.scale && co < P.Cout) v = v * __ldg(P.scale + co) + __ldg(P.shift + co);
-    if (P.relu) v = fmaxf(v, 0.f);
-    r.v[j] = v;
-  }
-  if (P.plain_out) {
-    reinterpret_cast<float*>(P.out)[(long long)b * Vo + vox] = r.v[0];
-    return;
-  }
   const int Gout = P.Cout / 8;
-  const size_t off = g8_offset(b, g, z, y, x, Gout, P.Dout, P.Hout, P.Wout);
-  if (P.skip) {
-    F8 s = load8(reinterpret_cast<const TOut*>(P.skip) + off);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r.v[j] += s.v[j];
+  for (int v = 0; v < kVX; ++v) {
+    const int x = x0 + v;
+    if (x >= P.Wout) break;
+    F8 r;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int co = g * 8 + j;
+      float t = acc[v][j];
+      if (P.scale && co < P.Cout) t = t * __ldg(P.scale + co) + __ldg(P.shift + co);
+      if (P.relu) t = fmaxf(t, 0.f);
+      r.v[j] = t;
+    }
+    if (P.plain_out) {
+      reinterpret_cast<float*>(P.out)[(long long)b * Vo + (long long)z * HWo + (long long)y * P.Wout + x] = r.v[0];
+      continue;
+    }
+    const size_t off = g8_offset(b, g, z, y, x, Gout, P.Dout, P.Hout, P.Wout);
+    if (P.skip) {
+      F8 sk = load8(reinterpret_cast<const TOut*>(P.skip) + off);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r.v[j] += sk.v[j];
+    }
+    store8(reinterpret_cast<TOut*>(P.out) + off, r);
   }
-  store8(reinterpret_cast<TOut*>(P.out) + off, r);
 }
 
 // PyTorch weight -> [Gout][27][Cin][8] fp32 (zero-padded to a multiple of 8 output channels)
@@ -158,8 +200,8 @@ int conv3d_direct_launch(const damvs_conv3d_desc* d, const void* in, const void*
     P.Dout = (d->Din - 1) / d->stride + 1; P.Hout = (d->Hin - 1) / d->stride + 1; P.Wout = (d->Win - 1) / d->stride + 1;
   }
   const int Gout = (d->Cout + 7) / 8;
-  const long long Vo = (long long)P.Dout * P.Hout * P.Wout;
-  dim3 grid((unsigned)((Vo + 127) / 128), Gout, d->B);
+  const long long Vq = (long long)P.Dout * P.Hout * ((P.Wout + kVX - 1) / kVX);   // one thread per quad of x-adjacent voxels
+  dim3 grid((unsigned)((Vq + 127) / 128), Gout, d->B);
   size_t smem = (size_t)27 * d->Cin * 8 * sizeof(float);
   if (smem > 200 * 1024) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d direct: Cin=%d too large", d->Cin);
 #define LAUNCH(TI, TO)                                                                                          \
