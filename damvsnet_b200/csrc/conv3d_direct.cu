@@ -25,13 +25,12 @@ struct ConvParams {
   int B, Cin, Cout, Din, Hin, Win, Dout, Hout, Wout, stride, transposed, relu, plain_out;
 };
 
-// VX consecutive output voxels along x per thread: every weight vector read from shared memory feeds 8 * VX FMAs instead
-// of 8 (the one-voxel version issued one LDS.128 per four FMAs and ran at 24 % of the fp32 peak).  Each output's own
-// arithmetic -- tap order (kd, kh, kw), channels in order inside a tap, two-level summation -- is unchanged, so the
-// results are bit-identical to the one-voxel kernel.
-constexpr int kVX = 4;
-
-template <typename TIn, typename TOut>
+// VX output voxels per thread, 32 apart along x (lane l of a warp owns x = strip * 32 * VX + v * 32 + l, v < VX): every
+// weight vector read from shared memory feeds 8 * VX FMAs instead of 8 (the one-voxel version issued one LDS.128 per four
+// FMAs and ran at 24 % of the fp32 peak), while the loads of one v stay coalesced across the warp (VX ADJACENT voxels per
+// thread put the lanes 128 bytes apart and made it slower).  Each output's own arithmetic -- tap order (kd, kh, kw),
+// channels in order inside a tap, two-level summation -- is unchanged: results are bit-identical to the one-voxel kernel.
+template <typename TIn, typename TOut, int kVX>
 __global__ void __launch_bounds__(128) conv3d_direct_kernel(const ConvParams P) {
   extern __shared__ float s_w[];  // [27][Cin][8]
   const int g = blockIdx.y, b = blockIdx.z;
@@ -42,16 +41,16 @@ __global__ void __launch_bounds__(128) conv3d_direct_kernel(const ConvParams P) 
     *reinterpret_cast<float4*>(s_w + i) = __ldg(reinterpret_cast<const float4*>(wsrc + i));
   __syncthreads();
 
-  const int Wq = (P.Wout + kVX - 1) / kVX;                 // x quads per output row
-  const long long HWq = (long long)P.Hout * Wq;
-  const long long Vq = HWq * P.Dout;
+  const int Ws = (P.Wout + 32 * kVX - 1) / (32 * kVX);     // strips of 32 * VX voxels per output row, one warp each
+  const long long HWs = (long long)P.Hout * Ws;
+  const long long Vs = HWs * P.Dout;
   const long long HWo = (long long)P.Hout * P.Wout;
   const long long Vo = HWo * P.Dout;
-  const long long vq = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (vq >= Vq) return;
-  const int z = (int)(vq / HWq);
-  const int rem = (int)(vq - (long long)z * HWq);
-  const int y = rem / Wq, x0 = (rem - y * Wq) * kVX;
+  const long long sid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (sid >= Vs) return;
+  const int z = (int)(sid / HWs);
+  const int rem = (int)(sid - (long long)z * HWs);
+  const int y = rem / Ws, x0 = (rem - y * Ws) * (32 * kVX) + (threadIdx.x & 31);
 
   float acc[kVX][8];
 #pragma unroll
@@ -85,7 +84,7 @@ __global__ void __launch_bounds__(128) conv3d_direct_kernel(const ConvParams P) 
         bool ok[kVX], any = false;
 #pragma unroll
         for (int v = 0; v < kVX; ++v) {
-          const int x = x0 + v;
+          const int x = x0 + 32 * v;
           if (P.transposed) {
             const int num = x + 1 - kw;
             xi[v] = num >> 1;
@@ -148,7 +147,7 @@ __global__ void __launch_bounds__(128) conv3d_direct_kernel(const ConvParams P) 
   const int Gout = P.Cout / 8;
 #pragma unroll
   for (int v = 0; v < kVX; ++v) {
-    const int x = x0 + v;
+    const int x = x0 + 32 * v;
     if (x >= P.Wout) break;
     F8 r;
 #pragma unroll
@@ -200,15 +199,21 @@ int conv3d_direct_launch(const damvs_conv3d_desc* d, const void* in, const void*
     P.Dout = (d->Din - 1) / d->stride + 1; P.Hout = (d->Hin - 1) / d->stride + 1; P.Wout = (d->Win - 1) / d->stride + 1;
   }
   const int Gout = (d->Cout + 7) / 8;
-  const long long Vq = (long long)P.Dout * P.Hout * ((P.Wout + kVX - 1) / kVX);   // one thread per quad of x-adjacent voxels
-  dim3 grid((unsigned)((Vq + 127) / 128), Gout, d->B);
+  // voxels per thread: as many as a row has 32-voxel strips to give (coarse levels are 50..100 wide)
+  const int vx = P.Wout >= 96 ? 4 : (P.Wout >= 48 ? 2 : 1);
+  const long long warps = (long long)P.Dout * P.Hout * ((P.Wout + 32 * vx - 1) / (32 * vx));
+  dim3 grid((unsigned)((warps * 32 + 127) / 128), Gout, d->B);
   size_t smem = (size_t)27 * d->Cin * 8 * sizeof(float);
   if (smem > 200 * 1024) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d direct: Cin=%d too large", d->Cin);
-#define LAUNCH(TI, TO)                                                                                          \
+#define LAUNCH_V(TI, TO, VX)                                                                                    \
   do {                                                                                                          \
     if (smem > 48 * 1024)                                                                                       \
-      DAMVS_CUDA_OK(cudaFuncSetAttribute(conv3d_direct_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv3d_direct_kernel<TI, TO><<<grid, 128, smem, st>>>(P);                                                   \
+      DAMVS_CUDA_OK(cudaFuncSetAttribute(conv3d_direct_kernel<TI, TO, VX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    conv3d_direct_kernel<TI, TO, VX><<<grid, 128, smem, st>>>(P);                                               \
+  } while (0)
+#define LAUNCH(TI, TO)                                                                                          \
+  do {                                                                                                          \
+    if (vx == 4) LAUNCH_V(TI, TO, 4); else if (vx == 2) LAUNCH_V(TI, TO, 2); else LAUNCH_V(TI, TO, 1);          \
   } while (0)
   const bool out_f32 = d->plain_out || d->out_dtype == DAMVS_F32;
   const int od = out_f32 ? DAMVS_F32 : d->out_dtype;
@@ -221,6 +226,7 @@ int conv3d_direct_launch(const damvs_conv3d_desc* d, const void* in, const void*
   else if (d->in_dtype == DAMVS_F16 && od == DAMVS_F16) LAUNCH(__half, __half);
   else return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d direct: in_dtype %d -> out_dtype %d not supported", d->in_dtype, d->out_dtype);
 #undef LAUNCH
+#undef LAUNCH_V
   DAMVS_LAUNCH_OK("conv3d_direct kernel");
   return DAMVS_OK;
 }
