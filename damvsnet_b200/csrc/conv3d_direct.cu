@@ -11,6 +11,9 @@
 // Mapping: a thread owns one output voxel and one group of 8 output channels;
 // the 27*Cin*8 weights of that group sit in shared memory and are read as
 // warp-wide broadcasts; input voxels are 8-channel vectors of the G8 volume.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace damvs {
@@ -30,7 +33,9 @@ struct ConvParams {
 // FMAs and ran at 24 % of the fp32 peak), while the loads of one v stay coalesced across the warp (VX ADJACENT voxels per
 // thread put the lanes 128 bytes apart and made it slower).  Each output's own arithmetic -- tap order (kd, kh, kw),
 // channels in order inside a tap, two-level summation -- is unchanged: results are bit-identical to the one-voxel kernel.
-template <typename TIn, typename TOut, int kVX>
+// ONE = the `prob` layer (one output channel, plain fp32 output): only channel 0 of the zero-padded weight group is
+// computed (the general path spent 7/8 of that layer's FMAs on the padding).
+template <typename TIn, typename TOut, int kVX, bool ONE>
 __global__ void __launch_bounds__(128) conv3d_direct_kernel(const ConvParams P) {
   extern __shared__ float s_w[];  // [27][Cin][8]
   const int g = blockIdx.y, b = blockIdx.z;
@@ -118,6 +123,12 @@ __global__ void __launch_bounds__(128) conv3d_direct_kernel(const ConvParams P) 
           }
 #pragma unroll
           for (int ci = 0; ci < 8; ++ci) {
+            if (ONE) {
+              const float w0 = wt[(gi * 8 + ci) * 8];
+#pragma unroll
+              for (int v = 0; v < kVX; ++v) part[v][0] = fmaf(val[v].v[ci], w0, part[v][0]);
+              continue;
+            }
             const float4 wa = *reinterpret_cast<const float4*>(wt + (gi * 8 + ci) * 8);
             const float4 wb = *reinterpret_cast<const float4*>(wt + (gi * 8 + ci) * 8 + 4);
 #pragma unroll
@@ -200,7 +211,10 @@ int conv3d_direct_launch(const damvs_conv3d_desc* d, const void* in, const void*
   }
   const int Gout = (d->Cout + 7) / 8;
   // voxels per thread: as many as a row has 32-voxel strips to give (coarse levels are 50..100 wide)
-  const int vx = P.Wout >= 96 ? 4 : (P.Wout >= 48 ? 2 : 1);
+  // measured on B200 (fp32 pipeline at the DTU-test shape): 34.1 / 43.0 / 41.7 views/s for 1 / 2 / 4 voxels per thread
+  // (4 costs occupancy: 128 registers), hence 2 wherever a row has two 32-voxel strips
+  static const int vx_cap = getenv("DAMVS_DIRECT_VX") ? atoi(getenv("DAMVS_DIRECT_VX")) : 2;   // development knob
+  const int vx = std::min(vx_cap, P.Wout >= 96 ? 4 : (P.Wout >= 48 ? 2 : 1));
   const long long warps = (long long)P.Dout * P.Hout * ((P.Wout + 32 * vx - 1) / (32 * vx));
   dim3 grid((unsigned)((warps * 32 + 127) / 128), Gout, d->B);
   size_t smem = (size_t)27 * d->Cin * 8 * sizeof(float);
@@ -208,14 +222,16 @@ int conv3d_direct_launch(const damvs_conv3d_desc* d, const void* in, const void*
 #define LAUNCH_V(TI, TO, VX)                                                                                    \
   do {                                                                                                          \
     if (smem > 48 * 1024)                                                                                       \
-      DAMVS_CUDA_OK(cudaFuncSetAttribute(conv3d_direct_kernel<TI, TO, VX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    conv3d_direct_kernel<TI, TO, VX><<<grid, 128, smem, st>>>(P);                                               \
+      DAMVS_CUDA_OK(cudaFuncSetAttribute(conv3d_direct_kernel<TI, TO, VX, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    if (one) conv3d_direct_kernel<TI, TO, VX, true><<<grid, 128, smem, st>>>(P);                                \
+    else conv3d_direct_kernel<TI, TO, VX, false><<<grid, 128, smem, st>>>(P);                                   \
   } while (0)
 #define LAUNCH(TI, TO)                                                                                          \
   do {                                                                                                          \
     if (vx == 4) LAUNCH_V(TI, TO, 4); else if (vx == 2) LAUNCH_V(TI, TO, 2); else LAUNCH_V(TI, TO, 1);          \
   } while (0)
   const bool out_f32 = d->plain_out || d->out_dtype == DAMVS_F32;
+  const bool one = d->plain_out && smem <= 48 * 1024;   // Cout == 1 (checked by the C ABI); Cin <= 48 keeps the default smem limit
   const int od = out_f32 ? DAMVS_F32 : d->out_dtype;
   if (d->in_dtype == DAMVS_F32 && od == DAMVS_F32) LAUNCH(float, float);
   else if (d->in_dtype == DAMVS_F32 && od == DAMVS_BF16) LAUNCH(float, __nv_bfloat16);
