@@ -46,16 +46,19 @@ __global__ void __launch_bounds__(128) conv3d_direct_kernel(const ConvParams P) 
     *reinterpret_cast<float4*>(s_w + i) = __ldg(reinterpret_cast<const float4*>(wsrc + i));
   __syncthreads();
 
-  const int Ws = (P.Wout + 32 * kVX - 1) / (32 * kVX);     // strips of 32 * VX voxels per output row, one warp each
-  const long long HWs = (long long)P.Hout * Ws;
-  const long long Vs = HWs * P.Dout;
+  // CTA = 4 warps = 4 consecutive output rows of one strip of 32 * VX voxels: the kh taps of a row are the rows its sibling
+  // warps load, so they hit in L1 (one row per CTA left every tap but kw to L2)
+  const int Ws = (P.Wout + 32 * kVX - 1) / (32 * kVX);     // strips per output row
+  const int Hb = (P.Hout + 3) / 4;                          // row blocks
+  const long long per_plane = (long long)Hb * Ws;
   const long long HWo = (long long)P.Hout * P.Wout;
   const long long Vo = HWo * P.Dout;
-  const long long sid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (sid >= Vs) return;
-  const int z = (int)(sid / HWs);
-  const int rem = (int)(sid - (long long)z * HWs);
-  const int y = rem / Ws, x0 = (rem - y * Ws) * (32 * kVX) + (threadIdx.x & 31);
+  const long long cid = blockIdx.x;                         // (z, row block, strip)
+  const int z = (int)(cid / per_plane);
+  const int rem = (int)(cid - (long long)z * per_plane);
+  const int y = (rem / Ws) * 4 + (threadIdx.x >> 5);
+  const int x0 = (rem % Ws) * (32 * kVX) + (threadIdx.x & 31);
+  if (z >= P.Dout || y >= P.Hout) return;
 
   float acc[kVX][8];
 #pragma unroll
@@ -215,8 +218,9 @@ int conv3d_direct_launch(const damvs_conv3d_desc* d, const void* in, const void*
   // (4 costs occupancy: 128 registers), hence 2 wherever a row has two 32-voxel strips
   static const int vx_cap = getenv("DAMVS_DIRECT_VX") ? atoi(getenv("DAMVS_DIRECT_VX")) : 2;   // development knob
   const int vx = std::min(vx_cap, P.Wout >= 96 ? 4 : (P.Wout >= 48 ? 2 : 1));
-  const long long warps = (long long)P.Dout * P.Hout * ((P.Wout + 32 * vx - 1) / (32 * vx));
-  dim3 grid((unsigned)((warps * 32 + 127) / 128), Gout, d->B);
+  const long long ctas = (long long)P.Dout * ((P.Hout + 3) / 4) * ((P.Wout + 32 * vx - 1) / (32 * vx));
+  if (ctas > 0x7fffffffll) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d direct: volume too large for one launch");
+  dim3 grid((unsigned)ctas, Gout, d->B);
   size_t smem = (size_t)27 * d->Cin * 8 * sizeof(float);
   if (smem > 200 * 1024) return set_error(DAMVS_ERR_UNSUPPORTED, "conv3d direct: Cin=%d too large", d->Cin);
 #define LAUNCH_V(TI, TO, VX)                                                                                    \
