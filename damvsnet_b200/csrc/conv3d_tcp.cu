@@ -14,9 +14,10 @@
 // an exchange through shared memory between the warps of a half (rows are warps).  The tile is 8 x 32 input
 // positions -> 6 x 30 outputs.  Slots are zeroed by the epilogue after draining, so every MMA accumulates.
 //
-// Warp roles (576 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-17 epilogue in four groups of
-// four; group g drains the output planes with global index = g mod 4, so the planes two iterations complete are
-// drained concurrently.  Measured (DAMVS_TCP_DBG phase elimination): the issuer's instruction
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer (one thread), warps 2-9 epilogue in two groups of
+// four; group g drains the output planes with global index = g mod 2, so the two planes an iteration completes are
+// drained concurrently (four groups / 16 epilogue warps measured slower: their barrier spinning takes issue slots from
+// the issuer).  Measured (DAMVS_TCP_DBG phase elimination): the issuer's instruction
 // path per iteration is what bounds these kernels once the A reads are gone, hence one wait for the planes, one for
 // the accumulator pair, at most four MMAs and ONE commit per iteration (the same barrier frees the shared-memory slot
 // for the producer and publishes the completed output planes to the epilogue).
@@ -68,7 +69,7 @@ struct Params {
 
 __device__ __forceinline__ float shfl_dn(uint32_t v, int d) { return __uint_as_float(__shfl_down_sync(0xffffffffu, v, d)); }
 constexpr size_t kSmemBase = 45 * 1024;   // offset of the fused head's logits buffer (>= the base kernel's footprint)
-constexpr int NG = 2;            // epilogue groups of four warps; group g drains the output planes with global index = g mod 4
+constexpr int NG = 2;            // epilogue groups of four warps; group g drains the output planes with global index = g mod NG
 constexpr int THREADS = 64 + NG * 128;
 __device__ __forceinline__ void group_barrier(int g) {   // constant ids: a register id would reserve all 16 barriers
   if (g == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
