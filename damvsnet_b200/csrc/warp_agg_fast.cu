@@ -28,6 +28,7 @@
 namespace damvs {
 
 constexpr int kMaxSrcH = 15;
+constexpr int kAggGwc = 2;   // internal MODE value: group-wise correlation (not in the reference; damvs_warp_gwc_fwd)
 
 struct WarpAggHParams {
   const __half* ref;
@@ -98,13 +99,24 @@ __device__ __forceinline__ void fhfma8(float (&out)[8], const float (&in)[8], co
   }
 }
 
+__device__ __forceinline__ void store1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void store1(__half* p, float v) { *reinterpret_cast<unsigned short*>(p) = (unsigned short)(pack_f16x2(v, 0.f) & 0xffffu); }
+
 __device__ __forceinline__ uint4 ldg16(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 
 // CPT = channels per thread (8 or 16): with 16 a thread owns two G8 groups -- the per-(view, hypothesis) overheads
 // (footprint exchange, tap addressing, the weight-net chain, loop control) are amortised over twice the channels, which
 // is what an instruction-issue-bound kernel needs (stage 2: 220 -> ~155 instructions per (view, voxel, 16 channels)).
-template <int C, int CPT, int MODE, typename OutT, int DCH, bool REUSE, int MINB, bool FULL>
+template <int C, int CPT, int MODE, typename OutT, int DCH, bool REUSE, int MINB, bool FULL, int G = 0>
 __global__ void __launch_bounds__(128, MINB) warp_agg_h_kernel(const WarpAggHParams P) {
+  // group-wise correlation (MODE == kAggGwc, CPT == 8): G groups of GS channels; a thread's 8 channels cover NV groups,
+  // or an eighth / quarter / half of one group that LPG adjacent lanes finish with shuffles
+  constexpr int GS = G > 0 ? C / G : 8;
+  constexpr int NV = GS >= 8 ? 1 : 8 / GS;
+  constexpr int LPG = GS >= 8 ? GS / 8 : 1;
+  constexpr int GOUT = G > 0 && G < 8 ? 8 : (G > 0 ? G : 8);
+  static_assert(MODE != kAggGwc || (CPT == 8 && G > 0), "group-wise correlation runs with 8 channels per thread");
   constexpr int NG = CPT / 8;      // G8 groups per thread
   constexpr int HP = CPT / 2;      // channel pairs per thread
   constexpr int LPP = C / CPT;     // lanes per pixel
@@ -166,6 +178,13 @@ __global__ void __launch_bounds__(128, MINB) warp_agg_h_kernel(const WarpAggHPar
 
   for (int d0 = 0; d0 < D; d0 += DCH) {
     float2 acc[DCH][HP], sq[MODE == DAMVS_AGG_VARIANCE ? DCH : 1][HP];
+    float accg[MODE == kAggGwc ? DCH : 1][NV];
+    if (MODE == kAggGwc) {
+#pragma unroll
+      for (int j = 0; j < DCH; ++j)
+#pragma unroll
+        for (int k = 0; k < NV; ++k) accg[j][k] = 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < DCH; ++j)
 #pragma unroll
@@ -233,11 +252,31 @@ __global__ void __launch_bounds__(128, MINB) warp_agg_h_kernel(const WarpAggHPar
           for (int n = 0; n < NG; ++n) {
             float df[8], base[8];   // warp - ref  (variance mode: warp)
 #pragma unroll
-            for (int k = 0; k < 8; ++k) base[k] = MODE == DAMVS_AGG_VARIANCE ? 0.f : nrf[n * 8 + k];
+            for (int k = 0; k < 8; ++k) base[k] = MODE == DAMVS_AGG_ADAPTIVE ? nrf[n * 8 + k] : 0.f;
             fhfma8<false>(df, base, t00[n], f.w01);
             fhfma8<true>(df, df, t01[n], f.w01);
             fhfma8<false>(df, df, t10[n], f.w23);
             fhfma8<true>(df, df, t11[n], f.w23);
+            if (MODE == kAggGwc) {
+              float pr[8];                                   // ref * warp (nrf holds -ref)
+#pragma unroll
+              for (int k = 0; k < 8; ++k) pr[k] = -nrf[k] * df[k];
+              if (GS >= 8) {
+                float s = ((pr[0] + pr[1]) + (pr[2] + pr[3])) + ((pr[4] + pr[5]) + (pr[6] + pr[7]));
+#pragma unroll
+                for (int o = LPG / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                accg[j][0] += s;
+              } else {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) {
+                  float s = 0.f;
+#pragma unroll
+                  for (int i = 0; i < GS; ++i) s += pr[k * GS + i];
+                  accg[j][k] += s;
+                }
+              }
+              continue;
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const float2 d2 = make_float2(df[2 * k], df[2 * k + 1]);
@@ -250,7 +289,7 @@ __global__ void __launch_bounds__(128, MINB) warp_agg_h_kernel(const WarpAggHPar
               }
             }
           }
-          if (MODE != DAMVS_AGG_VARIANCE) {
+          if (MODE == DAMVS_AGG_ADAPTIVE) {
             float s = sv.x + sv.y;
 #pragma unroll
             for (int o = LPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -263,6 +302,41 @@ __global__ void __launch_bounds__(128, MINB) warp_agg_h_kernel(const WarpAggHPar
         }
       }
       if (LPP > 1) __syncwarp();  // footprints of this view are consumed before the next view overwrites them
+    }
+    if (MODE == kAggGwc) {
+      const float norm = 1.f / ((float)n_src * (float)GS);
+      OutT* og = reinterpret_cast<OutT*>(P.out);
+#pragma unroll
+      for (int j = 0; j < DCH; ++j) {
+        if (!(FULL || d0 + j < D) || !live) continue;
+        if (GS >= 8) {
+          if (q % LPG == 0) {
+            const int ch = q / LPG;
+            OutT* o = og + g8_offset(b, ch / 8, d0 + j, y, x, GOUT / 8, D, H, W) + (ch % 8);
+            store1(o, accg[j][0] * norm);
+            if (G < 8) store1(o + G, 0.f);                    // zero padding channels (G = 4)
+          }
+        } else {
+          const int ch0 = q * NV;
+          OutT* o = og + g8_offset(b, ch0 / 8, d0 + j, y, x, GOUT / 8, D, H, W) + (ch0 % 8);
+          if (NV == 8) {
+            F8 r;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) r.v[k] = accg[j][k] * norm;
+            store8(o, r);
+          } else if (NV == 4) {
+            store4(o, accg[j][0] * norm, accg[j][1] * norm, accg[j][2] * norm, accg[j][3] * norm);
+          } else {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) store1(o + k, accg[j][k] * norm);
+          }
+          if (G < 8) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) store1(o + G + k, 0.f);
+          }
+        }
+      }
+      continue;
     }
 #pragma unroll
     for (int j = 0; j < DCH; ++j) {
@@ -373,6 +447,40 @@ static int launch_h(const WarpAggHParams& P, int out_dtype, cudaStream_t st) {
   static const int cfg = getenv("DAMVS_WARP_CFG") ? atoi(getenv("DAMVS_WARP_CFG")) : 0;   // development knob
   if (C >= 16 && cfg == 16) return launch_h_cfg<C, MODE, (C >= 16 ? 16 : 8), 2, 4>(P, out_dtype, st);   // 16 channels per thread
   return launch_h_cfg<C, MODE, HCfg<C>::CPT, HCfg<C>::DCH, HCfg<C>::MINB>(P, out_dtype, st);
+}
+
+// Group-wise correlation on the tuned kernel (fp16 features, 2-byte volume, D a multiple of the depth chunk); called by
+// damvs_warp_gwc_fwd (warp_gwc.cu), which keeps the plain kernel for every other case.
+template <int C, int G>
+static int launch_gwc_fast_cg(const WarpAggHParams& P, int out_dtype, cudaStream_t st) {
+  constexpr int DCH = HCfg<C>::DCH, MINB = HCfg<C>::MINB;
+  constexpr int TW = 32 / (C / 8), TH = 4;
+  dim3 grid((P.W + TW - 1) / TW, (P.H + TH - 1) / TH, P.B);
+  if (out_dtype == DAMVS_F16) warp_agg_h_kernel<C, 8, kAggGwc, __half, DCH, false, MINB, true, G><<<grid, 128, 0, st>>>(P);
+  else warp_agg_h_kernel<C, 8, kAggGwc, __nv_bfloat16, DCH, false, MINB, true, G><<<grid, 128, 0, st>>>(P);
+  DAMVS_LAUNCH_OK("warp_agg_h kernel (group-wise correlation)");
+  return DAMVS_OK;
+}
+
+bool warp_gwc_fast_supported(int C, int G, int D, int n_src, int feat_dtype, int out_dtype) {
+  static const bool off = getenv("DAMVS_GWC_PLAIN") != nullptr;   // development knob: A/B against warp_gwc.cu's kernel
+  const int dch = C == 32 ? HCfg<32>::DCH : (C == 16 ? HCfg<16>::DCH : HCfg<8>::DCH);
+  return !off && feat_dtype == DAMVS_F16 && (out_dtype == DAMVS_F16 || out_dtype == DAMVS_BF16) && D % dch == 0 && n_src <= kMaxSrcH;
+}
+
+int warp_gwc_fast_launch(const void* ref, const void* const* src, int n_src, const float* rot_trans, const float* hyp, void* out, int B, int C,
+                         int G, int D, int H, int W, int per_pixel, int out_dtype, cudaStream_t st) {
+  WarpAggHParams P;
+  P.ref = (const __half*)ref;
+  for (int v = 0; v < kMaxSrcH; ++v) P.src[v] = v < n_src ? (const __half*)src[v] : nullptr;
+  P.rot_trans = rot_trans; P.hyp = hyp; P.wnet = nullptr; P.out = out;
+  P.B = B; P.n_src = n_src; P.D = D; P.H = H; P.W = W; P.per_pixel = per_pixel;
+#define GO(CC, GG) if (C == CC && G == GG) return launch_gwc_fast_cg<CC, GG>(P, out_dtype, st)
+  GO(8, 4); GO(8, 8);
+  GO(16, 4); GO(16, 8); GO(16, 16);
+  GO(32, 4); GO(32, 8); GO(32, 16); GO(32, 32);
+#undef GO
+  return set_error(DAMVS_ERR_UNSUPPORTED, "warp_gwc (fast): C=%d, G=%d not supported", C, G);
 }
 
 }  // namespace damvs

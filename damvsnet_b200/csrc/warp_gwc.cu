@@ -189,6 +189,11 @@ static int launch_gwc(const GwcParams& P, int feat_dtype, int out_dtype, cudaStr
   return feat_dtype == DAMVS_F16 ? launch_gwc_t<C, G, __half>(P, out_dtype, st) : launch_gwc_t<C, G, float>(P, out_dtype, st);
 }
 
+// the tuned fp16-feature kernel with a group-wise epilogue (warp_agg_fast.cu)
+bool warp_gwc_fast_supported(int C, int G, int D, int n_src, int feat_dtype, int out_dtype);
+int warp_gwc_fast_launch(const void* ref, const void* const* src, int n_src, const float* rot_trans, const float* hyp, void* out, int B, int C,
+                         int G, int D, int H, int W, int per_pixel, int out_dtype, cudaStream_t st);
+
 }  // namespace damvs
 
 using namespace damvs;
@@ -203,6 +208,11 @@ extern "C" int damvs_warp_gwc_fwd(const void* ref_nhwc, const void* const* src_n
   DAMVS_REQUIRE(feat_dtype == DAMVS_F32 || feat_dtype == DAMVS_F16, "warp_gwc: features must be fp32 or fp16 NHWC (feat_dtype %d)", feat_dtype);
   DAMVS_REQUIRE(out_dtype == DAMVS_F32 || out_dtype == DAMVS_BF16 || out_dtype == DAMVS_F16, "warp_gwc: bad out_dtype %d", out_dtype);
   DAMVS_REQUIRE(aligned16(ref_nhwc) && aligned16(out_vol), "warp_gwc: ref and out must be 16-byte aligned");
+  for (int v = 0; v < n_src; ++v) DAMVS_REQUIRE(src_nhwc[v] && aligned16(src_nhwc[v]), "warp_gwc: src[%d] null or not 16-byte aligned", v);
+  if ((long long)H * W * C * 2 < (1ll << 31) && warp_gwc_fast_supported(C, G, D, n_src, feat_dtype, out_dtype) &&
+      (C == 8 || C == 16 || C == 32) && (G == 4 || G == 8 || G == 16 || G == 32) && G <= C)
+    return warp_gwc_fast_launch(ref_nhwc, src_nhwc, n_src, rot_trans, depth_hyp, out_vol, B, C, G, D, H, W, per_pixel_hyp, out_dtype,
+                                (cudaStream_t)stream);
   GwcParams P;
   P.ref = ref_nhwc;
   for (int v = 0; v < kMaxSrcG; ++v) P.src[v] = v < n_src ? src_nhwc[v] : nullptr;
