@@ -402,7 +402,7 @@ def incumbent_gpu_leg(args, dev, dev_stages, sd, iters=3):
     return out
 
 
-def full_forward_leg(args, dev, sd, iters=3):
+def full_forward_leg(args, dev, sd, iters=3, with_reference=True, seed=0):
     """Full CascadeMVSNet.forward (models/cas_mvsnet.py:190-319), images in pinned host memory -> output dict, final
     depth + confidence read back to the host (test_uni.py:229-237): the reference as is on this GPU, then the SAME class
     with the hot path re-bound to this package by dropin.install() (FPN / GeoFeatureFusion stay the reference's PyTorch)."""
@@ -414,8 +414,8 @@ def full_forward_leg(args, dev, sd, iters=3):
     from damvsnet_b200 import synthetic
     nd = [int(x) for x in args.ndepths.split(",")]
     H, W, N = args.height, args.width, args.nviews
-    imgs = synthetic.make_images(1, N, H, W, seed=0).pin_memory()
-    projs, intr = synthetic.make_cameras(1, N, H, W, seed=0)
+    imgs = synthetic.make_images(1, N, H, W, seed=seed).pin_memory()
+    projs, intr = synthetic.make_cameras(1, N, H, W, seed=seed)
     dvals = synthetic.make_depth_range(1, 192)
     out = {"what": f"CascadeMVSNet.forward {H}x{W} N={N} D={args.ndepths}: imgs [1,{N},3,{H},{W}] fp32 from pinned host memory "
                    "(H2D inside the timed region), stage-3 depth + confidence read back; random-init FPN / GeoFeatureFusion "
@@ -445,8 +445,10 @@ def full_forward_leg(args, dev, sd, iters=3):
     try:
         ref_model = ref_loader.build_cascade(nd, args.mode, hot_state_dict=sd).to(dev)
         state = ref_model.state_dict()
-        sec, d_ref = timed(ref_model)
-        out["reference_torch_defaults"] = {"views_s": 1.0 / sec, "ms_per_view": sec * 1e3}
+        d_ref = None
+        if with_reference:
+            sec, d_ref = timed(ref_model)
+            out["reference_torch_defaults"] = {"views_s": 1.0 / sec, "ms_per_view": sec * 1e3}
         del ref_model
         torch.cuda.empty_cache()
         dropin.install(precision=args.precision)
@@ -459,7 +461,9 @@ def full_forward_leg(args, dev, sd, iters=3):
             ours = ours.eval().to(dev)
             sec, d_ours = timed(ours)
             out["dropin_" + args.precision] = {"views_s": 1.0 / sec, "ms_per_view": sec * 1e3}
-            out["final_depth_median_rel_diff"] = ((d_ours - d_ref).abs() / d_ref.abs().clamp_min(1.0)).median().item()
+            out["_sec"] = sec
+            if d_ref is not None:
+                out["final_depth_median_rel_diff"] = ((d_ours - d_ref).abs() / d_ref.abs().clamp_min(1.0)).median().item()
             del ours
         finally:
             dropin.uninstall()
@@ -773,13 +777,22 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             extras["train_samples_s"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         dm.set_precision(args.precision, args.conv_impl)
-        # (4) full forward, images in -> dict out, reference vs drop-in (rank 0, N = 1)
-        if rank == 0 and world == 1:
-            try:
-                extras["full_forward"] = full_forward_leg(args, dev, sd)
-            except Exception as exc:  # noqa: BLE001
-                extras["full_forward"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-            dm.set_precision(args.precision, args.conv_impl)
+        # (4) full forward, images in -> dict out: the drop-in on every rank (one view stream per GPU, sharded like the hot
+        #     path; throughput = ranks / slowest rank's seconds per view), the unmodified reference beside it on rank 0 at N = 1
+        try:
+            ff = full_forward_leg(args, dev, sd, with_reference=(rank == 0 and world == 1), seed=rank)
+        except Exception as exc:  # noqa: BLE001
+            ff = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+        dm.set_precision(args.precision, args.conv_impl)
+        sec_t = torch.tensor([ff.pop("_sec", -1.0) if isinstance(ff, dict) else -1.0], dtype=torch.float64, device=dev)
+        bad_t = (sec_t < 0).to(torch.float64)
+        if world > 1:
+            dist.all_reduce(sec_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bad_t, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            if bad_t.item() == 0 and sec_t.item() > 0:
+                ff["dropin_" + args.precision] = {"views_s": world / sec_t.item(), "ms_per_view_slowest_rank": sec_t.item() * 1e3, "ranks": world}
+            extras["full_forward"] = ff
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
