@@ -12,4 +12,4 @@ from .module import (AggWeightNetVolume, Conv3d, CostRegNet, Deconv3d, depth_reg
 from .losses import cross_view_loss  # noqa: F401
 from .ops import G8Volume, precision, set_precision  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
