@@ -197,3 +197,22 @@ def test_tnt_full_size_seven_views_matches_oracle(dm, stage, D):
             assert e["depth_rel_median"] <= b_med and e["depth_rel_p99"] <= b_p99 and e["depth_rel_max"] <= b_max and e["prob_max"] <= b_prob, (prec, e)
         else:
             assert e["depth_rel_p99"] <= 1e-4 and e["depth_rel_max"] <= 5e-4 and e["prob_max"] <= 2e-2, (prec, e)
+
+
+def test_dtu_full_size_variance_aggregation_stage3(dm):
+    """agg_mode="variance" (reference models/cas_mvsnet.py:34-37, 61-63, 84-85) at the full DTU-test stage-3 grid
+    (1152x1600, N=5, D=8), every precision mode against the oracle."""
+    from damvsnet_b200 import synthetic
+    from damvsnet_b200.runner import HotPathRunner
+    sd = {k: v for k, v in calibrated_state_dict().items() if not k.startswith("DepthNet.")}
+    f, p, d = synthetic.make_stage_inputs(2, 1, 5, 1152, 1600, 8, seed=4)
+    want = O.depthnet_forward(2, f, p, d, sd, "variance")
+    runner = HotPathRunner(sd, mode="variance", device=DEV)
+    for prec in ("fp32", "fp16", "bf16"):
+        with dm.precision(prec):
+            o = runner.run_stage(2, [x.to(DEV) for x in f], p.to(DEV), d.to(DEV))
+        e = stage_errors(o, want, d)
+        if prec == "fp32":
+            assert e["depth_rel_max"] <= 2e-4 and e["depth_rel_p99"] <= 5e-5 and e["prob_max"] <= 2e-3, e
+        else:
+            assert e["depth_rel_p99"] <= 1e-4 and e["depth_rel_max"] <= 5e-4 and e["prob_max"] <= 3e-2, (prec, e)
