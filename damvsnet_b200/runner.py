@@ -98,7 +98,7 @@ class HotPathRunner:
         buffers (pointers and shapes are baked in: callers refill the same tensors between calls).
         One graph launch replaces ~60 kernel launches + ~70 small torch ops of host work per view."""
         from . import ops
-        key = (self._signature(stages), ops.get_precision(), ops._POLICY["conv_impl"])
+        key = (self._signature(stages),) + tuple(sorted(ops._POLICY.items()))     # every policy knob that shapes the captured step
         hit = self._graphs.get(key)
         if hit is None:
             # warm-up outside capture: weight packing synchronises and fills the per-module caches

@@ -55,11 +55,11 @@ def dtu(dm):
     return sd, stages, want
 
 
-def _run(dm, sd, stages, prec, only=None):
+def _run(dm, sd, stages, prec, only=None, features="auto"):
     from damvsnet_b200.runner import HotPathRunner
     runner = HotPathRunner(sd, device=DEV)
     outs = []
-    with dm.precision(prec):
+    with dm.precision(prec, features=features):
         for s, (f, p, d) in enumerate(stages):
             if only is not None and s != only:
                 outs.append(None)
@@ -114,6 +114,17 @@ def test_dtu_full_size_half_precision_within_stated_bound(dm, dtu, prec):
             assert e["depth_rel_p99"] <= 1e-4 and e["depth_rel_max"] <= 5e-4, (s, e)
         for k in ("depth", "photometric_confidence", "variance", "prob_volume"):
             assert torch.isfinite(o[k]).all(), (s, k)
+
+
+def test_dtu_full_size_fp16_convs_with_fp32_features_meet_the_survey_bound(dm, dtu):
+    """set_precision("fp16", features="fp32"): the gather stays in fp32, the cost volume and CostRegNet run in fp16 on the
+    tensor cores.  This is the configuration SURVEY.md H7's bound was written for (reduced precision on the convolutions
+    only): per stage depth rel p99 <= 1e-3, max <= 5e-3, confidence abs p99 <= 1e-2 -- met at full size on the peaked net."""
+    sd, stages, want = dtu
+    outs = _run(dm, sd, stages, "fp16", features="fp32")
+    for s, (o, w) in enumerate(zip(outs, want)):
+        e = stage_errors(o, w, stages[s][2])
+        assert e["depth_rel_p99"] <= 1e-3 and e["depth_rel_max"] <= 5e-3 and e["conf_p99"] <= 1e-2 and e["prob_max"] <= 2e-2, (s, e)
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="oracle/_ref was not staged with this tree")
