@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/damvs.h"
 
@@ -47,6 +48,13 @@ inline int current_sm_count() {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
   if (dev < 64) cache[dev] = n;
   return n;
+}
+
+// Development knob DAMVS_TC_GRID_PCT: cap the persistent conv grids at pct % of (CTAs per SM x SMs), so that some SMs
+// keep room for other streams' kernels (experiment of DESIGN.md section 6; 100 = off).
+inline int tc_grid_cap(int ctas) {
+  static const int pct = getenv("DAMVS_TC_GRID_PCT") ? atoi(getenv("DAMVS_TC_GRID_PCT")) : 100;
+  return pct >= 100 ? ctas : (ctas * pct + 99) / 100;
 }
 
 // ---- G8 volume addressing ---------------------------------------------------

@@ -815,7 +815,7 @@ static int launch_one(const damvs_conv3d_desc* d, TcParams& P, const void* in, c
   static const int occ_cap = getenv("DAMVS_TC_OCC") ? atoi(getenv("DAMVS_TC_OCC")) : 8;   // development knob
   occ = std::min(occ, occ_cap);
   const int num_sms = current_sm_count();
-  dim3 grid((unsigned)std::min(P.ntiles, occ * num_sms), 1, 1);
+  dim3 grid((unsigned)std::min(P.ntiles, tc_grid_cap(occ * num_sms)), 1, 1);
 #ifdef DAMVS_TC_TRACE_BUILD
   // Development aid, compiled ONLY into a -DDAMVS_TC_TRACE_BUILD library: timestamps of a few CTAs, printed to stderr.
   // It allocates and synchronises, which the product C ABI never does (and which would break graph capture).

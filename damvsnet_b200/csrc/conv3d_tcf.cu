@@ -366,7 +366,7 @@ static int launch_g(const damvs_conv3d_desc* d, Params& P, const void* in, cudaS
   P.ntiles = P.tiles_x * P.tiles_y * d->B;
   const int num_sms = current_sm_count();
   static const int occ_cap = getenv("DAMVS_TC_OCC") ? atoi(getenv("DAMVS_TC_OCC")) : 2;   // development knob
-  dim3 grid((unsigned)std::min(P.ntiles, std::min(2, occ_cap) * num_sms), 1, 1);
+  dim3 grid((unsigned)std::min(P.ntiles, tc_grid_cap(std::min(2, occ_cap) * num_sms)), 1, 1);
   kern<<<grid, 320, smem, st>>>(m0, P);
   DAMVS_LAUNCH_OK("conv3d_tcf kernel");
   return DAMVS_OK;
